@@ -1,0 +1,231 @@
+"""Host-side mirror of ds2i's Index / wand_data / query-operator interface over the C ABI.
+
+Names and argument meaning follow the reference (queries.hpp, block_freq_index.hpp, wand_data.hpp):
+an operator object is called as ``op(index, terms)`` and returns what the reference operator
+returns (match count for and/or, ``topk().size()`` for the ranked ones); ``op.topk()`` gives the
+scores.  ``op.batch(index, queries)`` evaluates a whole list of queries in one device launch —
+that is the product path; the single-query call is a batch of one.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+
+OPS = ("and", "and_freq", "or", "or_freq", "ranked_and", "wand", "maxscore", "ranked_or")
+RANKED = ("ranked_and", "wand", "maxscore", "ranked_or")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _flatten(queries):
+    offs = np.zeros(len(queries) + 1, dtype=np.uint64)
+    if len(queries):
+        offs[1:] = np.cumsum([len(q) for q in queries], dtype=np.uint64)
+    flat = np.fromiter((t for q in queries for t in q), dtype=np.uint32, count=int(offs[-1])) if len(queries) else np.zeros(0, np.uint32)
+    if flat.size == 0:
+        flat = np.zeros(1, np.uint32)[:0]
+    return np.ascontiguousarray(flat), offs
+
+
+class Index:
+    """An index file of type `index_type` (index_types.hpp:41) resident in HBM of `device`."""
+
+    def __init__(self, path, index_type, device=0):
+        self._h = C.c_void_p()
+        self.index_type = index_type
+        L = _native.lib()
+        _native.check(L.ds2i_gpu_index_open_file(str(path).encode(), index_type.encode(), device, C.byref(self._h)))
+
+    @classmethod
+    def from_bytes(cls, data, index_type, device=0):
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.index_type = index_type
+        buf = (C.c_char * len(data)).from_buffer_copy(data)
+        _native.check(_native.lib().ds2i_gpu_index_open(C.cast(buf, C.c_void_p), len(data), index_type.encode(), device, C.byref(self._h)))
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _native.lib().ds2i_gpu_index_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return int(_native.lib().ds2i_gpu_index_size(self._h))
+
+    def num_docs(self):
+        return int(_native.lib().ds2i_gpu_index_num_docs(self._h))
+
+    def device_bytes(self):
+        return int(_native.lib().ds2i_gpu_index_device_bytes(self._h))
+
+    def list_sizes(self, terms):
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        out = np.zeros(len(terms), dtype=np.uint64)
+        _native.check(_native.lib().ds2i_gpu_index_list_sizes(self._h, _p(terms, C.c_uint32), len(terms), _p(out, C.c_uint64)))
+        return out
+
+    def decode_lists(self, terms):
+        """docid()/freq() of every posting of index[term], as next() delivers them.
+        Returns (offsets, docs, freqs, elapsed_ms)."""
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        sizes = self.list_sizes(terms)
+        offs = np.zeros(len(terms) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(sizes, dtype=np.uint64)
+        total = int(offs[-1])
+        docs = np.zeros(max(total, 1), dtype=np.uint32)
+        freqs = np.zeros(max(total, 1), dtype=np.uint32)
+        ms = C.c_float()
+        _native.check(_native.lib().ds2i_gpu_decode_lists(self._h, _p(terms, C.c_uint32), len(terms), _p(offs, C.c_uint64),
+                                                       _p(docs, C.c_uint32), _p(freqs, C.c_uint32), C.byref(ms)))
+        return offs, docs[:total], freqs[:total], ms.value
+
+    def next_geq_batch(self, terms, bounds_per_list):
+        """index[term] opened, then next_geq(b) for each b (non-decreasing).  Returns (docids, freqs, ms)."""
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        flat, offs = _flatten64(bounds_per_list)
+        n = int(offs[-1])
+        docids = np.zeros(max(n, 1), dtype=np.uint64)
+        freqs = np.zeros(max(n, 1), dtype=np.uint64)
+        ms = C.c_float()
+        _native.check(_native.lib().ds2i_gpu_next_geq_batch(self._h, _p(terms, C.c_uint32), len(terms), _p(flat, C.c_uint64),
+                                                         _p(offs, C.c_uint64), _p(docids, C.c_uint64), _p(freqs, C.c_uint64), C.byref(ms)))
+        return docids[:n], freqs[:n], ms.value
+
+
+def _flatten64(lists):
+    offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+    if len(lists):
+        offs[1:] = np.cumsum([len(b) for b in lists], dtype=np.uint64)
+    flat = np.concatenate([np.asarray(b, dtype=np.uint64) for b in lists]) if len(lists) and int(offs[-1]) else np.zeros(1, np.uint64)
+    return np.ascontiguousarray(flat), offs
+
+
+class WandData:
+    """wand_data<bm25> (wand_data.hpp) resident in HBM."""
+
+    def __init__(self, path, device=0):
+        self._h = C.c_void_p()
+        _native.check(_native.lib().ds2i_gpu_wand_open_file(str(path).encode(), device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _native.lib().ds2i_gpu_wand_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class QueryBatch:
+    """A batch of queries resident in HBM (ds2i_gpu_batch_*): prepare once, run several operators."""
+
+    def __init__(self, index, wdata, queries):
+        self._h = C.c_void_p()
+        self.nq = len(queries)
+        self._keep = (index, wdata)
+        flat, offs = _flatten(queries)
+        wh = wdata._h if wdata is not None else C.c_void_p()
+        _native.check(_native.lib().ds2i_gpu_batch_prepare(index._h, wh, _p(flat, C.c_uint32), _p(offs, C.c_uint64), self.nq, C.byref(self._h)))
+        self.h2d_bytes = flat.nbytes + offs.nbytes
+
+    def run(self, op, k=10):
+        ms = C.c_float()
+        self._k = k
+        self._op = op
+        _native.check(_native.lib().ds2i_gpu_batch_run(self._h, OPS.index(op), k, C.byref(ms)))
+        return ms.value
+
+    def fetch(self):
+        counts = np.zeros(max(self.nq, 1), dtype=np.uint64)
+        scores = np.zeros((max(self.nq, 1), self._k), dtype=np.float32)
+        _native.check(_native.lib().ds2i_gpu_batch_fetch(self._h, _p(counts, C.c_uint64), _p(scores, C.c_float)))
+        return counts[:self.nq], scores[:self.nq]
+
+    def stats(self):
+        s = np.zeros(8, dtype=np.uint64)
+        _native.check(_native.lib().ds2i_gpu_batch_stats(self._h, _p(s, C.c_uint64)))
+        keys = ("docs_blocks", "freqs_blocks", "docs_bytes", "freqs_bytes", "block_maxs_read", "docs_scored", "launches")
+        return {k: int(v) for k, v in zip(keys, s)}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _native.lib().ds2i_gpu_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def query_batch(index, wdata, op, queries, k=10):
+    """One call, host buffers in and out (ds2i_gpu_query_batch).  Returns (counts, scores, elapsed_ms)."""
+    flat, offs = _flatten(queries)
+    nq = len(queries)
+    counts = np.zeros(max(nq, 1), dtype=np.uint64)
+    scores = np.zeros((max(nq, 1), k), dtype=np.float32)
+    ms = C.c_float()
+    wh = wdata._h if wdata is not None else C.c_void_p()
+    _native.check(_native.lib().ds2i_gpu_query_batch(index._h, wh, OPS.index(op), k, _p(flat, C.c_uint32), _p(offs, C.c_uint64), nq,
+                                                  _p(counts, C.c_uint64), _p(scores, C.c_float), C.byref(ms)))
+    return counts[:nq], scores[:nq], ms.value
+
+
+class _Operator:
+    name = None
+
+    def __init__(self, wdata=None, k=10):
+        self._wdata = wdata
+        self._k = k
+        self._topk = np.zeros(0, dtype=np.float32)
+
+    def __call__(self, index, terms):
+        counts, scores, _ = query_batch(index, self._wdata, self.name, [list(terms)], self._k)
+        if self.name in RANKED:
+            self._topk = scores[0][: int(counts[0])].copy()
+        return int(counts[0])
+
+    def batch(self, index, queries):
+        return query_batch(index, self._wdata, self.name, queries, self._k)
+
+    def topk(self):
+        return self._topk
+
+
+def _mk(opname):
+    return type(opname + "_query", (_Operator,), {"name": opname})
+
+
+and_query = _mk("and")
+and_freq_query = _mk("and_freq")
+or_query = _mk("or")
+or_freq_query = _mk("or_freq")
+ranked_and_query = _mk("ranked_and")
+wand_query = _mk("wand")
+maxscore_query = _mk("maxscore")
+ranked_or_query = _mk("ranked_or")
+
+
+def read_queries(path, limit=None):
+    """read_query (queries.hpp:15-27): one query per line, whitespace-separated term ids."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            out.append([int(t) for t in line.split()])
+            if limit is not None and len(out) >= limit:
+                break
+    return out

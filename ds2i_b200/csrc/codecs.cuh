@@ -1,0 +1,168 @@
+// Warp-cooperative decoders of ds2i's block codecs, reading the compressed bytes from a
+// shared-memory window that TMA staged (device_common.cuh).  One warp decodes one block of up to
+// 128 integers; every function is warp-collective (all 32 lanes call it with the same arguments)
+// and returns, warp-uniformly, the number of bytes the block occupies — the reference decoders
+// return the pointer past the block (block_codecs.hpp:127-147,210-226,287-314,336-349) and the
+// freqs block starts exactly there (block_posting_list.hpp:304-307).
+#pragma once
+#include "device_common.cuh"
+
+namespace ds2i_gpu {
+
+enum : int { CODEC_OPTPFOR = 0, CODEC_VARINT = 1, CODEC_INTERPOLATIVE = 2, CODEC_QMX = 3 };
+
+constexpr uint32_t BLOCK = 128;            // BlockCodec::block_size for every codec
+constexpr uint32_t SCRATCH_WORDS = 320;    // Simple16 output (<= 2*128 + 27) / interpolative stack
+
+// ---- Simple16 layouts (FastPFor/headers/simple16.h:730-1110) ----------------------------------
+// selector -> up to three runs (count, bits); values fill the 28 payload bits MSB-first.
+// packed as n1 | b1<<5 | n2<<10 | b2<<15 | n3<<20 | b3<<25
+#define S16(n1, b1, n2, b2, n3, b3) \
+    (uint32_t(n1) | (uint32_t(b1) << 5) | (uint32_t(n2) << 10) | (uint32_t(b2) << 15) | (uint32_t(n3) << 20) | (uint32_t(b3) << 25))
+__device__ __constant__ uint32_t c_s16_layout[16] = {
+    S16(28, 1, 0, 0, 0, 0), S16(7, 2, 14, 1, 0, 0), S16(7, 1, 7, 2, 7, 1), S16(14, 1, 7, 2, 0, 0),
+    S16(14, 2, 0, 0, 0, 0), S16(1, 4, 8, 3, 0, 0),  S16(1, 3, 4, 4, 3, 3), S16(7, 4, 0, 0, 0, 0),
+    S16(4, 5, 2, 4, 0, 0),  S16(2, 4, 4, 5, 0, 0),  S16(3, 6, 2, 5, 0, 0), S16(2, 5, 3, 6, 0, 0),
+    S16(4, 7, 0, 0, 0, 0),  S16(1, 10, 2, 9, 0, 0), S16(2, 14, 0, 0, 0, 0), S16(1, 28, 0, 0, 0, 0)};
+#undef S16
+
+__device__ __forceinline__ void s16_table_init(uint32_t* tab /* 16 words of shared memory */) {
+    if (threadIdx.x < 16) tab[threadIdx.x] = c_s16_layout[threadIdx.x];
+}
+__device__ __forceinline__ uint32_t s16_count(uint32_t lay) {
+    return (lay & 31u) + ((lay >> 10) & 31u) + ((lay >> 20) & 31u);
+}
+// j-th value of a Simple16 word
+__device__ __forceinline__ uint32_t s16_value(uint32_t word, uint32_t lay, uint32_t j) {
+    uint32_t n1 = lay & 31u, b1 = (lay >> 5) & 31u, n2 = (lay >> 10) & 31u, b2 = (lay >> 15) & 31u, b3 = lay >> 25;
+    uint32_t off, w;
+    if (j < n1) { off = j * b1; w = b1; }
+    else if (j < n1 + n2) { off = n1 * b1 + (j - n1) * b2; w = b2; }
+    else { off = n1 * b1 + n2 * b2 + (j - n1 - n2) * b3; w = b3; }
+    return (word >> (28u - off - w)) & ((1u << w) - 1u);
+}
+
+// ---- TightVariableByte, one value (block_codecs.hpp:84-98); single-lane helper -----------------
+__device__ __forceinline__ uint32_t vbyte_decode(const uint32_t* win, uint32_t& off) {
+    uint32_t v = 0;
+#pragma unroll 1
+    for (uint32_t shift = 0; shift <= 28; shift += 7) {
+        uint32_t c = lds_u8(win, off++);
+        v += (c & 127u) << shift;
+        if (c & 128u) break;
+    }
+    return v;
+}
+
+// ---- OptPFD / NewPFD block of exactly 128 values (FastPFor/headers/newpfor.h:254-286) ---------
+// Header word b<<26 | nExc<<16 | excWords; Simple16 exception stream; 4 groups of 32 values packed
+// LSB-first at b bits (bitpackinghelpers.h fastunpack).  Lane l unpacks element l of each group;
+// the byte phase of the (unaligned) block is folded into the bit position, so no realignment pass.
+__device__ __forceinline__ uint32_t decode_optpfor128(const uint32_t* win, uint32_t off, uint32_t* out,
+                                                      uint32_t* scratch, const uint32_t* s16tab) {
+    const unsigned lane = lane_id();
+    const uint32_t w0 = lds_u32(win, off);
+    const uint32_t b = w0 >> 26;
+    const uint32_t nexc = (w0 >> 16) & 0x3ffu;
+    const uint32_t excw = w0 & 0xffffu;
+    if (b >= 32) {   // raw block: newpfor.h:204-209
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) out[32 * j + lane] = lds_u32(win, off + 4u * (1u + 32u * j + lane));
+        __syncwarp();
+        return 4u * 129u;
+    }
+    const uint32_t pbit = 8u * (off + 4u * (1u + excw)) + lane * b;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) out[32 * j + lane] = lds_bits(win, pbit + 32u * b * j, b);
+
+    if (nexc) {
+        // Simple16: lane per word, warp scan of the per-word counts, each lane expands its word.
+        uint32_t* E = scratch;
+        const uint32_t need = 2u * nexc;
+        uint32_t produced = 0;
+        for (uint32_t base = 0; base < excw && produced < need; base += 32) {
+            uint32_t w = base + lane;
+            bool valid = w < excw;
+            uint32_t word = valid ? lds_u32(win, off + 4u * (1u + w)) : 0u;
+            uint32_t lay = s16tab[word >> 28];
+            uint32_t cnt = valid ? s16_count(lay) : 0u;
+            uint32_t incl = warp_inclusive_scan(cnt);
+            uint32_t start = produced + incl - cnt;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                uint32_t idx = start + j;
+                if (idx < SCRATCH_WORDS) E[idx] = s16_value(word, lay, j);
+            }
+            produced += __shfl_sync(FULL, incl, 31);
+        }
+        __syncwarp();
+        // exceptions: first half = position gaps - 1 (first absolute), second half = high bits - 1
+        uint32_t carry = 0;
+        for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
+            uint32_t e = e0 + lane;
+            uint32_t g = e < nexc ? E[e] + 1u : 0u;
+            uint32_t incl = warp_inclusive_scan(g);
+            uint32_t p = carry + incl - 1u;
+            if (e < nexc && p < BLOCK) out[p] |= (E[nexc + e] + 1u) << b;
+            carry += __shfl_sync(FULL, incl, 31);
+        }
+    }
+    __syncwarp();
+    return 4u * (1u + excw + 4u * b);
+}
+
+// ---- Binary interpolative block, n <= 128 (interpolative_coding.hpp:93-146) -------------------
+// Bit-serial: each code length depends on previously decoded values, so lane 0 decodes while the
+// warp waits.  Writes the PREFIX SUMS P[0..n-1] (P[n-1] = sum) into out; callers turn them into
+// docids (base + P[i] + i) or freqs (P[i] - P[i-1]) in parallel.
+__device__ __forceinline__ uint32_t decode_interpolative_prefix(const uint32_t* win, uint32_t off, uint32_t n,
+                                                                uint32_t sum_of_values, uint32_t* out,
+                                                                uint32_t* scratch) {
+    uint32_t consumed = 0;
+    if (lane_id() == 0) {
+        uint32_t pos = off;
+        uint32_t sum = sum_of_values;
+        if (sum == 0xffffffffu) sum = vbyte_decode(win, pos);
+        out[n - 1] = sum;
+        uint32_t bits = 0;
+        if (n > 1) {
+            const uint32_t bitbase = 8u * pos;
+            uint32_t* stack = scratch;   // pending right halves: (base, cnt, low, high)
+            int sp = 0;
+            uint32_t base = 0, cnt = n - 1, low = 0, high = sum;
+            while (true) {
+                uint32_t h = cnt >> 1;
+                uint32_t u = high - low + 1u;
+                uint32_t val = 0;
+                if (u > 1u) {
+                    uint32_t nb = 31u - __clz(u);                               // msb(u)
+                    uint32_t m = (nb == 31u) ? (0u - u) : ((2u << nb) - u);      // 2^(nb+1) - u
+                    val = lds_bits(win, bitbase + bits, nb);
+                    bits += nb;
+                    if (val >= m) {
+                        uint32_t one = lds_bits(win, bitbase + bits, 1);
+                        bits += 1;
+                        val = (val << 1) + one - m;
+                    }
+                }
+                val += low;
+                out[base + h] = val;
+                uint32_t rc = cnt - h - 1u;
+                if (h) {
+                    if (rc) { stack[4 * sp] = base + h + 1u; stack[4 * sp + 1] = rc; stack[4 * sp + 2] = val; stack[4 * sp + 3] = high; ++sp; }
+                    cnt = h; high = val;                  // descend left: (base, h, low, val)
+                } else if (rc) {
+                    base = base + 1u; cnt = rc; low = val; // h == 0: go right directly
+                } else {
+                    if (!sp) break;
+                    --sp;
+                    base = stack[4 * sp]; cnt = stack[4 * sp + 1]; low = stack[4 * sp + 2]; high = stack[4 * sp + 3];
+                }
+            }
+        }
+        consumed = (pos - off) + ((bits + 7u) >> 3);
+    }
+    __syncwarp();
+    return __shfl_sync(FULL, consumed, 0);
+}
+
+}  // namespace ds2i_gpu

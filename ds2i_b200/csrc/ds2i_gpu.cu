@@ -1,0 +1,614 @@
+// libds2i_gpu.so — C ABI (include/ds2i_gpu.h) over the sm_100a kernels.  Host side: parse ds2i's
+// on-disk format, build the flat list directory, copy the compressed index once into HBM, turn
+// each query into the device descriptor (term order, host-computed BM25 query weights), launch.
+// There is no CPU fallback: without a CUDA device every entry point fails with DS2I_E_CUDA.
+#include "../../include/ds2i_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "format.hpp"
+#include "query_kernels.cuh"
+#include "pef_kernels.cuh"
+
+using namespace ds2i_gpu;
+
+static_assert(MAX_TERMS == DS2I_GPU_MAX_TERMS, "header/kernels disagree");
+static_assert(MAX_K == DS2I_GPU_MAX_K, "header/kernels disagree");
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, std::string const& msg) { g_last_error = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(DS2I_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+template <typename T>
+struct dev_buf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~dev_buf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    }
+    cudaError_t upload(std::vector<T> const& v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+struct mapped_file {
+    const uint8_t* p = nullptr; size_t n = 0;
+    ~mapped_file() { if (p) munmap(const_cast<uint8_t*>(p), n); }
+    bool open(const char* path) {
+        int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st; fstat(fd, &st); n = size_t(st.st_size);
+        void* m = n ? mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+        ::close(fd);
+        if (n && m == MAP_FAILED) { p = nullptr; return false; }
+        p = static_cast<const uint8_t*>(m);
+        return true;
+    }
+};
+
+enum : int { KIND_BLOCK = 0, KIND_PEF = 1 };
+
+struct ds2i_gpu_index {
+    int device = 0;
+    int kind = KIND_BLOCK;
+    int codec = CODEC_OPTPFOR;
+    uint64_t size = 0, num_docs = 0;
+    uint64_t device_bytes = 0;
+    // block indexes
+    std::vector<ListDir> host_dir;
+    dev_buf<uint8_t> d_lists;
+    dev_buf<ListDir> d_dir;
+    DevIndex dev{};
+    // opt (partitioned Elias-Fano) index
+    std::unique_ptr<PefIndexHost> pef;
+    int sm_count = 148;
+};
+
+struct ds2i_gpu_wand {
+    int device = 0;
+    uint64_t num_docs = 0, num_terms = 0;
+    std::vector<float> h_max_term_weight;
+    dev_buf<float> d_norm_lens, d_max_term_weight;
+    DevWand dev{};
+};
+
+struct ds2i_gpu_batch {
+    ds2i_gpu_index* index = nullptr;
+    ds2i_gpu_wand* wand = nullptr;
+    uint32_t nq = 0;
+    int max_terms = 1;
+    uint32_t last_k = 0;
+    bool last_ranked = false;
+    dev_buf<uint32_t> q_begin, term, sched, work_counter;
+    dev_buf<float> q_weight, max_weight, out_scores;
+    dev_buf<uint8_t> ord_size, ord_maxw;
+    dev_buf<uint64_t> out_counts;
+    dev_buf<unsigned long long> stats;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~ds2i_gpu_batch() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
+};
+
+static int codec_from_type(const char* t, int* kind) {
+    std::string s(t ? t : "");
+    *kind = KIND_BLOCK;
+    if (s == "block_optpfor") return CODEC_OPTPFOR;
+    if (s == "block_varint") return CODEC_VARINT;
+    if (s == "block_interpolative") return CODEC_INTERPOLATIVE;
+    if (s == "block_qmx") return CODEC_QMX;
+    if (s == "opt") { *kind = KIND_PEF; return 0; }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* ds2i_gpu_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int ds2i_gpu_op_from_name(const char* name) {
+    static const char* names[] = {"and", "and_freq", "or", "or_freq", "ranked_and", "wand", "maxscore", "ranked_or"};
+    if (!name) return DS2I_E_ARG;
+    for (int i = 0; i < 8; ++i) if (!strcmp(name, names[i])) return i;
+    return DS2I_E_ARG;
+}
+
+extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const char* index_type, int device,
+                                   ds2i_gpu_index** out) {
+    if (!file_bytes || !out || !index_type) return fail(DS2I_E_ARG, "null argument");
+    int kind;
+    int codec = codec_from_type(index_type, &kind);
+    if (codec < 0) return fail(DS2I_E_UNSUPPORTED, std::string("unsupported index type ") + index_type);
+    if (kind == KIND_BLOCK && (codec == CODEC_VARINT || codec == CODEC_QMX))
+        return fail(DS2I_E_UNSUPPORTED, std::string("index type not built yet: ") + index_type);
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<ds2i_gpu_index> ix(new ds2i_gpu_index);
+    ix->device = device; ix->kind = kind; ix->codec = codec;
+    cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device);
+    try {
+        const uint8_t* p = static_cast<const uint8_t*>(file_bytes);
+        if (kind == KIND_PEF) {
+            ix->pef.reset(new PefIndexHost);
+            std::string err;
+            int rc = ix->pef->load(p, nbytes, err);
+            if (rc != 0) return fail(rc, err);
+            ix->size = ix->pef->size; ix->num_docs = ix->pef->num_docs; ix->device_bytes = ix->pef->device_bytes;
+            *out = ix.release();
+            return DS2I_OK;
+        }
+        block_index_file f = parse_block_index(p, nbytes);
+        ix->size = f.size; ix->num_docs = f.num_docs;
+        // list directory: start offsets come from the Elias-Fano endpoints (block_freq_index.hpp:85-94)
+        std::vector<uint64_t> starts = ef_decode_all(f.endpoints, 0, f.lists_bytes, f.size, f.params);
+        ix->host_dir.resize(f.size);
+        const uint8_t* lists_end = f.lists + f.lists_bytes;
+        for (uint64_t i = 0; i < f.size; ++i) {
+            uint64_t begin = starts[i], end = (i + 1 < f.size) ? starts[i + 1] : f.lists_bytes;
+            if (begin >= end || end > f.lists_bytes) throw format_error("list endpoints out of order");
+            uint32_t n;
+            const uint8_t* q = tight_vbyte_decode(f.lists + begin, lists_end, &n);
+            if (!n) throw format_error("empty posting list");
+            uint64_t blocks = (uint64_t(n) + BLOCK - 1) / BLOCK;
+            uint64_t maxs_off = uint64_t(q - f.lists);
+            uint64_t data_off = maxs_off + 4 * blocks + 4 * (blocks - 1);
+            if (data_off > end) throw format_error("posting list header exceeds the list");
+            ix->host_dir[i] = ListDir{maxs_off, n, uint32_t(end - data_off)};
+        }
+        const size_t pad = 4096;   // staged windows and unaligned reads may run past the last list
+        CUDA_TRY(ix->d_lists.alloc(f.lists_bytes + pad));
+        CUDA_TRY(cudaMemcpy(ix->d_lists.p, f.lists, f.lists_bytes, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset(ix->d_lists.p + f.lists_bytes, 0, pad));
+        CUDA_TRY(ix->d_dir.upload(ix->host_dir));
+        ix->dev.lists = ix->d_lists.p; ix->dev.dir = ix->d_dir.p;
+        ix->dev.num_lists = f.size; ix->dev.num_docs = uint32_t(f.num_docs);
+        ix->device_bytes = f.lists_bytes + pad + f.size * sizeof(ListDir);
+    } catch (std::exception const& e) {
+        return fail(DS2I_E_FORMAT, e.what());
+    }
+    *out = ix.release();
+    return DS2I_OK;
+}
+
+extern "C" int ds2i_gpu_index_open_file(const char* path, const char* index_type, int device, ds2i_gpu_index** out) {
+    if (!path) return fail(DS2I_E_ARG, "null path");
+    mapped_file m;
+    if (!m.open(path)) return fail(DS2I_E_ARG, std::string("cannot open ") + path);
+    return ds2i_gpu_index_open(m.p, m.n, index_type, device, out);
+}
+
+extern "C" void ds2i_gpu_index_close(ds2i_gpu_index* ix) { delete ix; }
+extern "C" uint64_t ds2i_gpu_index_size(const ds2i_gpu_index* ix) { return ix ? ix->size : 0; }
+extern "C" uint64_t ds2i_gpu_index_num_docs(const ds2i_gpu_index* ix) { return ix ? ix->num_docs : 0; }
+extern "C" uint64_t ds2i_gpu_index_device_bytes(const ds2i_gpu_index* ix) { return ix ? ix->device_bytes : 0; }
+
+static inline uint64_t list_size_of(const ds2i_gpu_index* ix, uint32_t term) {
+    return ix->kind == KIND_PEF ? ix->pef->host_dir[term].n : ix->host_dir[term].n;
+}
+
+extern "C" int ds2i_gpu_index_list_sizes(const ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms, uint64_t* out_sizes) {
+    if (!ix || (!terms && nterms) || (!out_sizes && nterms)) return fail(DS2I_E_ARG, "null argument");
+    for (size_t i = 0; i < nterms; ++i) {
+        if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
+        out_sizes[i] = list_size_of(ix, terms[i]);
+    }
+    return DS2I_OK;
+}
+
+extern "C" int ds2i_gpu_wand_open(const void* file_bytes, size_t nbytes, int device, ds2i_gpu_wand** out) {
+    if (!file_bytes || !out) return fail(DS2I_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<ds2i_gpu_wand> w(new ds2i_gpu_wand);
+    w->device = device;
+    try {
+        wand_file f = parse_wand(static_cast<const uint8_t*>(file_bytes), nbytes);
+        w->num_docs = f.num_docs; w->num_terms = f.num_terms;
+        w->h_max_term_weight.resize(f.num_terms);
+        if (f.num_terms) memcpy(w->h_max_term_weight.data(), f.max_term_weight, f.num_terms * 4);
+        CUDA_TRY(w->d_norm_lens.alloc(f.num_docs));
+        if (f.num_docs) CUDA_TRY(cudaMemcpy(w->d_norm_lens.p, f.norm_lens, f.num_docs * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(w->d_max_term_weight.upload(w->h_max_term_weight));
+        w->dev.norm_lens = w->d_norm_lens.p; w->dev.max_term_weight = w->d_max_term_weight.p;
+    } catch (std::exception const& e) {
+        return fail(DS2I_E_FORMAT, e.what());
+    }
+    *out = w.release();
+    return DS2I_OK;
+}
+
+extern "C" int ds2i_gpu_wand_open_file(const char* path, int device, ds2i_gpu_wand** out) {
+    if (!path) return fail(DS2I_E_ARG, "null path");
+    mapped_file m;
+    if (!m.open(path)) return fail(DS2I_E_ARG, std::string("cannot open ") + path);
+    return ds2i_gpu_wand_open(m.p, m.n, device, out);
+}
+extern "C" void ds2i_gpu_wand_close(ds2i_gpu_wand* w) { delete w; }
+
+// ------------------------------------------------------------------------------------------------
+// bm25::query_term_weight (bm25.hpp:17-24), evaluated on the host with the same libm as the reference
+static float query_term_weight(uint64_t freq, uint64_t df, uint64_t num_docs) {
+    float f = float(freq);
+    float fdf = float(df);
+    float idf = std::log((float(num_docs) - fdf + 0.5f) / (fdf + 0.5f));
+    static const float epsilon_score = 1.0E-6f;
+    return f * std::max(epsilon_score, idf) * (1.0f + 1.2f);
+}
+
+extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uint32_t* terms,
+                                      const uint64_t* query_offsets, size_t nq, ds2i_gpu_batch** out) {
+    if (!ix || !out || !query_offsets || (!terms && nq && query_offsets[nq])) return fail(DS2I_E_ARG, "null argument");
+    if (nq > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many queries in one batch");
+    if (wand && wand->num_docs < ix->num_docs) return fail(DS2I_E_ARG, "wand data has fewer documents than the index");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    std::unique_ptr<ds2i_gpu_batch> b(new ds2i_gpu_batch);
+    b->index = ix; b->wand = wand; b->nq = uint32_t(nq);
+
+    std::vector<uint32_t> q_begin(nq + 1, 0), term, sched(nq);
+    std::vector<float> q_weight, max_weight;
+    std::vector<uint8_t> ord_size, ord_maxw;
+    std::vector<uint64_t> cost(nq, 0);
+    struct ent { uint64_t n; float mw; uint8_t pos; };
+    std::vector<uint32_t> tmp;
+    std::vector<ent> ents;
+    int max_terms = 1;
+    for (size_t q = 0; q < nq; ++q) {
+        if (query_offsets[q + 1] < query_offsets[q]) return fail(DS2I_E_ARG, "query_offsets not monotone");
+        tmp.assign(terms + query_offsets[q], terms + query_offsets[q + 1]);
+        std::sort(tmp.begin(), tmp.end());               // query_freqs (queries.hpp:136-150)
+        ents.clear();
+        for (size_t i = 0; i < tmp.size();) {
+            size_t j = i;
+            while (j < tmp.size() && tmp[j] == tmp[i]) ++j;
+            uint32_t t = tmp[i];
+            if (t >= ix->size) return fail(DS2I_E_ARG, "term id out of range in query " + std::to_string(q));
+            if (wand && t >= wand->num_terms) return fail(DS2I_E_ARG, "term id beyond wand data");
+            uint64_t n = list_size_of(ix, t);
+            float qw = query_term_weight(j - i, n, ix->num_docs);
+            float mw = wand ? qw * wand->h_max_term_weight[t] : 0.f;
+            if (ents.size() >= size_t(MAX_TERMS))
+                return fail(DS2I_E_LIMIT, "query " + std::to_string(q) + " has more than " + std::to_string(MAX_TERMS) + " distinct terms");
+            ents.push_back(ent{n, mw, uint8_t(ents.size())});
+            term.push_back(t); q_weight.push_back(qw); max_weight.push_back(mw);
+            cost[q] += n;
+            i = j;
+        }
+        max_terms = std::max<int>(max_terms, int(ents.size()));
+        q_begin[q + 1] = uint32_t(term.size());
+        // the reference's own std::sort calls, on the same keys in the same initial order
+        std::vector<ent> by_size(ents), by_mw(ents);
+        std::sort(by_size.begin(), by_size.end(), [](ent const& l, ent const& r) { return l.n < r.n; });
+        std::sort(by_mw.begin(), by_mw.end(), [](ent const& l, ent const& r) { return l.mw < r.mw; });
+        for (auto const& e : by_size) ord_size.push_back(e.pos);
+        for (auto const& e : by_mw) ord_maxw.push_back(e.pos);
+    }
+    std::iota(sched.begin(), sched.end(), 0u);
+    std::stable_sort(sched.begin(), sched.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+
+    b->max_terms = max_terms;
+    CUDA_TRY(b->q_begin.upload(q_begin)); CUDA_TRY(b->term.upload(term)); CUDA_TRY(b->sched.upload(sched));
+    CUDA_TRY(b->q_weight.upload(q_weight)); CUDA_TRY(b->max_weight.upload(max_weight));
+    CUDA_TRY(b->ord_size.upload(ord_size)); CUDA_TRY(b->ord_maxw.upload(ord_maxw));
+    CUDA_TRY(b->work_counter.alloc(1));
+    CUDA_TRY(b->out_counts.alloc(nq)); CUDA_TRY(b->out_scores.alloc(nq * MAX_K));
+    CUDA_TRY(b->stats.alloc(8));
+    CUDA_TRY(cudaMemset(b->stats.p, 0, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaEventCreate(&b->ev0)); CUDA_TRY(cudaEventCreate(&b->ev1));
+    *out = b.release();
+    return DS2I_OK;
+}
+
+template <int CODEC, int OP>
+static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
+    ds2i_gpu_index* ix = b->index;
+    const int warps = 4;
+    size_t smem = warps * warp_smem_bytes(b->max_terms);
+    auto kern = query_kernel<CODEC, OP>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return fail(DS2I_E_CUDA, "query kernel does not fit on an SM");
+    int grid = per_sm * ix->sm_count;
+    int needed = int((b->nq + warps - 1) / warps);
+    if (grid > needed) grid = std::max(needed, 1);
+    DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr};
+    kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, k, b->max_terms);
+    return DS2I_OK;
+}
+
+template <int CODEC>
+static int launch_query_op(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32_t k) {
+    switch (op) {
+        case OP_AND: return launch_query<CODEC, OP_AND>(b, db, k);
+        case OP_AND_FREQ: return launch_query<CODEC, OP_AND_FREQ>(b, db, k);
+        case OP_OR: return launch_query<CODEC, OP_OR>(b, db, k);
+        case OP_OR_FREQ: return launch_query<CODEC, OP_OR_FREQ>(b, db, k);
+        case OP_RANKED_AND: return launch_query<CODEC, OP_RANKED_AND>(b, db, k);
+        case OP_WAND: return launch_query<CODEC, OP_WAND>(b, db, k);
+        case OP_MAXSCORE: return launch_query<CODEC, OP_MAXSCORE>(b, db, k);
+        case OP_RANKED_OR: return launch_query<CODEC, OP_RANKED_OR>(b, db, k);
+    }
+    return fail(DS2I_E_ARG, "unknown operator");
+}
+
+extern "C" int ds2i_gpu_batch_run(ds2i_gpu_batch* b, int op, uint32_t k, float* out_elapsed_ms) {
+    if (!b) return fail(DS2I_E_ARG, "null batch");
+    if (op < 0 || op > OP_RANKED_OR) return fail(DS2I_E_ARG, "unknown operator");
+    const bool ranked = op >= OP_RANKED_AND;
+    if (ranked && !b->wand) return fail(DS2I_E_ARG, "ranked operators need wand data");
+    if (ranked && (k < 1 || k > MAX_K)) return fail(DS2I_E_LIMIT, "k must be in 1.." + std::to_string(MAX_K));
+    ds2i_gpu_index* ix = b->index;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    DevBatch db{};
+    db.nq = b->nq; db.q_begin = b->q_begin.p; db.term = b->term.p; db.q_weight = b->q_weight.p;
+    db.max_weight = b->max_weight.p; db.ord_size = b->ord_size.p; db.ord_maxw = b->ord_maxw.p;
+    db.sched = b->sched.p; db.work_counter = b->work_counter.p; db.out_counts = b->out_counts.p;
+    db.out_scores = b->out_scores.p; db.stats = b->stats.p;
+    CUDA_TRY(cudaMemsetAsync(b->stats.p, 0, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, sizeof(uint32_t)));
+    CUDA_TRY(cudaEventRecord(b->ev0));
+    int rc = DS2I_OK;
+    if (b->nq) {
+        if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
+        else if (ix->codec == CODEC_OPTPFOR) rc = launch_query_op<CODEC_OPTPFOR>(b, db, op, k);
+        else if (ix->codec == CODEC_INTERPOLATIVE) rc = launch_query_op<CODEC_INTERPOLATIVE>(b, db, op, k);
+        else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+        if (rc != DS2I_OK) return rc;
+        b->launches += 1;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev1));
+    CUDA_TRY(cudaEventSynchronize(b->ev1));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    if (out_elapsed_ms) *out_elapsed_ms = ms;
+    b->last_k = ranked ? k : 0; b->last_ranked = ranked;
+    return DS2I_OK;
+}
+
+extern "C" int ds2i_gpu_batch_fetch(ds2i_gpu_batch* b, uint64_t* out_counts, float* out_scores) {
+    if (!b) return fail(DS2I_E_ARG, "null batch");
+    CUDA_TRY(cudaSetDevice(b->index->device));
+    if (out_counts && b->nq) CUDA_TRY(cudaMemcpy(out_counts, b->out_counts.p, size_t(b->nq) * 8, cudaMemcpyDeviceToHost));
+    if (out_scores && b->nq && b->last_ranked)
+        CUDA_TRY(cudaMemcpy(out_scores, b->out_scores.p, size_t(b->nq) * b->last_k * 4, cudaMemcpyDeviceToHost));
+    return DS2I_OK;
+}
+
+extern "C" int ds2i_gpu_batch_stats(ds2i_gpu_batch* b, uint64_t out_stats[8]) {
+    if (!b || !out_stats) return fail(DS2I_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(b->index->device));
+    unsigned long long s[8];
+    CUDA_TRY(cudaMemcpy(s, b->stats.p, sizeof(s), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out_stats[i] = s[i];
+    out_stats[6] = b->launches;
+    return DS2I_OK;
+}
+
+extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { delete b; }
+
+extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int op, uint32_t k,
+                                    const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
+                                    uint64_t* out_counts, float* out_scores, float* out_elapsed_ms) {
+    ds2i_gpu_batch* b = nullptr;
+    int rc = ds2i_gpu_batch_prepare(ix, wand, terms, query_offsets, nq, &b);
+    if (rc != DS2I_OK) return rc;
+    std::unique_ptr<ds2i_gpu_batch> guard(b);
+    rc = ds2i_gpu_batch_run(b, op, k, out_elapsed_ms);
+    if (rc != DS2I_OK) return rc;
+    return ds2i_gpu_batch_fetch(b, out_counts, out_scores);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched block decode (BASELINE config 2): one warp per 128-posting block, any list, any order.
+struct DecodeJob {
+    const uint32_t* terms;        // nterms
+    const uint64_t* blk_prefix;   // nterms+1: blocks before list i
+    const uint64_t* out_offsets;  // nterms+1: postings before list i
+    uint32_t* out_docs;
+    uint32_t* out_freqs;
+    uint64_t total_blocks;
+    uint32_t nterms;
+};
+
+template <int CODEC>
+__global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, DecodeJob job) {
+    __shared__ __align__(16) uint8_t smem_raw[8 * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16)];
+    __shared__ uint32_t s16tab[16];
+    s16_table_init(s16tab);
+    __syncthreads();
+    typedef BlockEnum<CODEC> E;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* base = smem_raw + warp * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16);
+    ListState* st = reinterpret_cast<ListState*>(base);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(ListState));
+    uint32_t* scratch = stage + STAGE_WORDS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
+    WarpCtx c;
+    ctx_init(c, stage, scratch, bar, s16tab);
+
+    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
+    for (uint64_t g = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp; g < job.total_blocks; g += nwarps) {
+        // list containing global block g
+        uint32_t lo = 0, hi = job.nterms;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (job.blk_prefix[mid] <= g) lo = mid; else hi = mid;
+        }
+        const uint32_t b = uint32_t(g - job.blk_prefix[lo]);
+        ListDir d = idx.dir[job.terms[lo]];
+        uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+        __syncwarp();
+        if (lane == 0) {
+            st->maxs_off = d.maxs_off;
+            st->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
+            st->n = d.n; st->nblocks = nblocks; st->data_bytes = d.data_bytes;
+        }
+        __syncwarp();
+        E::decode_docs_block(c, idx, st, b);
+        E::decode_freqs_block(c, idx, st);
+        const uint32_t size = st->cur_size;
+        const uint64_t o = job.out_offsets[lo] + uint64_t(b) * BLOCK;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t i = 32 * j + lane;
+            if (i < size) {
+                job.out_docs[o + i] = st->docs[i];
+                job.out_freqs[o + i] = st->freqs[i] + 1u;
+            }
+        }
+    }
+}
+
+extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms,
+                                     const uint64_t* out_offsets, uint32_t* out_docs, uint32_t* out_freqs,
+                                     float* out_elapsed_ms) {
+    if (!ix || (!terms && nterms) || !out_offsets) return fail(DS2I_E_ARG, "null argument");
+    if (nterms > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many lists");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    std::vector<uint64_t> blk(nterms + 1, 0), offs(out_offsets, out_offsets + nterms + 1);
+    for (size_t i = 0; i < nterms; ++i) {
+        if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
+        uint64_t n = list_size_of(ix, terms[i]);
+        if (offs[i + 1] - offs[i] != n) return fail(DS2I_E_ARG, "out_offsets do not match the list sizes");
+        blk[i + 1] = blk[i] + (n + BLOCK - 1) / BLOCK;
+    }
+    const uint64_t total = offs[nterms];
+    dev_buf<uint32_t> d_terms, d_docs, d_freqs;
+    dev_buf<uint64_t> d_blk, d_offs;
+    std::vector<uint32_t> tv(terms, terms + nterms);
+    CUDA_TRY(d_terms.upload(tv)); CUDA_TRY(d_blk.upload(blk)); CUDA_TRY(d_offs.upload(offs));
+    CUDA_TRY(d_docs.alloc(total)); CUDA_TRY(d_freqs.alloc(total));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0));
+    int rc = DS2I_OK;
+    if (nterms && total) {
+        if (ix->kind == KIND_PEF) {
+            rc = pef_decode_lists(*ix->pef, d_terms.p, uint32_t(nterms), d_offs.p, d_docs.p, d_freqs.p, ix->sm_count, g_last_error);
+        } else {
+            DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
+            uint64_t want = (blk[nterms] + 7) / 8;
+            int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
+            if (ix->codec == CODEC_OPTPFOR) decode_blocks_kernel<CODEC_OPTPFOR><<<grid, 256>>>(ix->dev, job);
+            else if (ix->codec == CODEC_INTERPOLATIVE) decode_blocks_kernel<CODEC_INTERPOLATIVE><<<grid, 256>>>(ix->dev, job);
+            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != DS2I_OK) return rc;
+    if (out_elapsed_ms) *out_elapsed_ms = ms;
+    if (total && out_docs) CUDA_TRY(cudaMemcpy(out_docs, d_docs.p, total * 4, cudaMemcpyDeviceToHost));
+    if (total && out_freqs) CUDA_TRY(cudaMemcpy(out_freqs, d_freqs.p, total * 4, cudaMemcpyDeviceToHost));
+    return DS2I_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// next_geq sweeps (BASELINE config 3 harness, also the enumerator parity test): warp per list.
+struct GeqJob {
+    const uint32_t* terms;
+    const uint64_t* bounds;
+    const uint64_t* bound_offsets;
+    uint64_t* out_docids;
+    uint64_t* out_freqs;
+    uint32_t* work_counter;
+    uint32_t nlists;
+};
+
+template <int CODEC>
+__global__ void __launch_bounds__(128) next_geq_kernel(DevIndex idx, GeqJob job) {
+    __shared__ __align__(16) uint8_t smem_raw[4 * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16)];
+    __shared__ uint32_t s16tab[16];
+    s16_table_init(s16tab);
+    __syncthreads();
+    typedef BlockEnum<CODEC> E;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* base = smem_raw + warp * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16);
+    ListState* st = reinterpret_cast<ListState*>(base);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(ListState));
+    uint32_t* scratch = stage + STAGE_WORDS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
+    WarpCtx c;
+    ctx_init(c, stage, scratch, bar, s16tab);
+    while (true) {
+        uint32_t li = 0;
+        if (lane == 0) li = atomicAdd(job.work_counter, 1u);
+        li = __shfl_sync(FULL, li, 0);
+        if (li >= job.nlists) break;
+        E::open(c, idx, st, job.terms[li]);
+        for (uint64_t j = job.bound_offsets[li]; j < job.bound_offsets[li + 1]; ++j) {
+            uint64_t lb = job.bounds[j];
+            uint32_t d = lb >= idx.num_docs ? E::next_geq(c, idx, st, idx.num_docs) : E::next_geq(c, idx, st, uint32_t(lb));
+            uint32_t f = d < idx.num_docs ? E::freq(c, idx, st) : 0u;
+            if (lane == 0) { job.out_docids[j] = d; job.out_freqs[j] = f; }
+        }
+    }
+}
+
+extern "C" int ds2i_gpu_next_geq_batch(ds2i_gpu_index* ix, const uint32_t* terms, size_t nlists,
+                                       const uint64_t* bounds, const uint64_t* bound_offsets,
+                                       uint64_t* out_docids, uint64_t* out_freqs, float* out_elapsed_ms) {
+    if (!ix || (!terms && nlists) || !bound_offsets) return fail(DS2I_E_ARG, "null argument");
+    if (nlists > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many lists");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    for (size_t i = 0; i < nlists; ++i)
+        if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
+    const uint64_t total = nlists ? bound_offsets[nlists] : 0;
+    std::vector<uint32_t> tv(terms, terms + nlists);
+    std::vector<uint64_t> bv(bounds, bounds + total), ov(bound_offsets, bound_offsets + nlists + 1);
+    dev_buf<uint32_t> d_terms, d_counter;
+    dev_buf<uint64_t> d_bounds, d_offs, d_docids, d_freqs;
+    CUDA_TRY(d_terms.upload(tv)); CUDA_TRY(d_bounds.upload(bv)); CUDA_TRY(d_offs.upload(ov));
+    CUDA_TRY(d_docids.alloc(total)); CUDA_TRY(d_freqs.alloc(total)); CUDA_TRY(d_counter.alloc(1));
+    CUDA_TRY(cudaMemset(d_counter.p, 0, 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0));
+    int rc = DS2I_OK;
+    if (nlists) {
+        if (ix->kind == KIND_PEF) {
+            rc = pef_next_geq(*ix->pef, d_terms.p, uint32_t(nlists), d_bounds.p, d_offs.p, d_docids.p, d_freqs.p, d_counter.p, ix->sm_count, g_last_error);
+        } else {
+            GeqJob job{d_terms.p, d_bounds.p, d_offs.p, d_docids.p, d_freqs.p, d_counter.p, uint32_t(nlists)};
+            int grid = int(std::min<uint64_t>((nlists + 3) / 4, uint64_t(ix->sm_count) * 8));
+            if (ix->codec == CODEC_OPTPFOR) next_geq_kernel<CODEC_OPTPFOR><<<grid, 128>>>(ix->dev, job);
+            else if (ix->codec == CODEC_INTERPOLATIVE) next_geq_kernel<CODEC_INTERPOLATIVE><<<grid, 128>>>(ix->dev, job);
+            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != DS2I_OK) return rc;
+    if (out_elapsed_ms) *out_elapsed_ms = ms;
+    if (total && out_docids) CUDA_TRY(cudaMemcpy(out_docids, d_docids.p, total * 8, cudaMemcpyDeviceToHost));
+    if (total && out_freqs) CUDA_TRY(cudaMemcpy(out_freqs, d_freqs.p, total * 8, cudaMemcpyDeviceToHost));
+    return DS2I_OK;
+}
