@@ -154,6 +154,22 @@ class QueryBatch:
         _native.check(_native.lib().ds2i_gpu_batch_fetch(self._h, _p(counts, C.c_uint64), _p(scores, C.c_float)))
         return counts[:self.nq], scores[:self.nq]
 
+    def device_results(self, k=None):
+        """(counts, scores) of the last run as torch CUDA tensors that alias the library's device buffers."""
+        import torch
+        k = self._k if k is None else k
+        pc, ps = C.c_void_p(), C.c_void_p()
+        _native.check(_native.lib().ds2i_gpu_batch_device_results(self._h, C.byref(pc), C.byref(ps)))
+
+        class _Cai:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        counts = torch.as_tensor(_Cai(pc.value, (self.nq,), "<i8"), device=dev)
+        scores = torch.as_tensor(_Cai(ps.value, (self.nq, k), "<f4"), device=dev)
+        return counts, scores
+
     def stats(self):
         s = np.zeros(8, dtype=np.uint64)
         _native.check(_native.lib().ds2i_gpu_batch_stats(self._h, _p(s, C.c_uint64)))

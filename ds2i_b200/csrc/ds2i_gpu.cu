@@ -404,6 +404,13 @@ extern "C" int ds2i_gpu_batch_stats(ds2i_gpu_batch* b, uint64_t out_stats[8]) {
     return DS2I_OK;
 }
 
+extern "C" int ds2i_gpu_batch_device_results(ds2i_gpu_batch* b, void** d_counts, void** d_scores) {
+    if (!b) return fail(DS2I_E_ARG, "null batch");
+    if (d_counts) *d_counts = b->out_counts.p;
+    if (d_scores) *d_scores = b->out_scores.p;
+    return DS2I_OK;
+}
+
 extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { delete b; }
 
 extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int op, uint32_t k,

@@ -95,6 +95,9 @@ int ds2i_gpu_batch_fetch(ds2i_gpu_batch*, uint64_t* out_counts, float* out_score
  * [2] compressed docs bytes, [3] compressed freqs bytes, [4] block_max entries read,
  * [5] documents scored, [6] kernel launches.  These are the algorithmic bytes of SURVEY.md §8(d). */
 int ds2i_gpu_batch_stats(ds2i_gpu_batch*, uint64_t out_stats[8]);
+/* Device addresses of the last run's results (counts: nq u64; scores: nq*k f32), for callers that
+ * hand them to a collective (NCCL gather of per-shard top-k) without a host round trip. */
+int ds2i_gpu_batch_device_results(ds2i_gpu_batch*, void** d_counts, void** d_scores);
 void ds2i_gpu_batch_free(ds2i_gpu_batch*);
 
 /* ---- Enumerator-level entry points (document_enumerator, block_posting_list.hpp:105-186) -------

@@ -213,6 +213,7 @@ int cmd_bench(int argc, char** argv)
     // scheme of profile_queries.cpp:21-39: thread t takes queries t, t+n, ...; one operator per thread
     double best = 1e300;
     uint64_t checksum = 0;
+    std::string pass_list;
     for (size_t pass = 0; pass < passes; ++pass) {
         std::vector<uint64_t> sums(n_threads, 0);
         auto t0 = std::chrono::steady_clock::now();
@@ -229,13 +230,14 @@ int cmd_bench(int argc, char** argv)
         for (auto& th : threads) th.join();
         double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         best = std::min(best, secs);
+        char tmp[64]; snprintf(tmp, sizeof tmp, "%s%.6f", pass ? ", " : "", secs); pass_list += tmp;
         checksum = 0;
         for (auto s : sums) checksum += s;
     }
     printf("{\"type\": \"%s\", \"query\": \"%s\", \"threads\": %zu, \"queries\": %zu, \"seconds\": %.6f, "
-           "\"qps\": %.3f, \"checksum\": %llu}\n",
+           "\"qps\": %.3f, \"checksum\": %llu, \"pass_seconds\": [%s]}\n",
            argv[2], op.c_str(), n_threads, queries.size(), best, queries.size() / best,
-           (unsigned long long)checksum);
+           (unsigned long long)checksum, pass_list.c_str());
     return 0;
 }
 
