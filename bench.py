@@ -211,6 +211,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    launches0 = batch.stats()["launches"]
     kernel_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -269,7 +270,7 @@ def main():
                    "parallelism": "query batch sharded over %d GPU(s), index replicated, NCCL all_gather of top-k" % world},
         "clocks": clocks.summary(),
         "e2e": {"value": nq_total / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": stats["launches"] if False else args.steps,
+        "gpu_launches": stats["launches"] - launches0,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch(args.op),
                      "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
                      "counters": stats},

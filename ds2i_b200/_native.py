@@ -12,7 +12,7 @@ SYMBOLS = [
     "ds2i_gpu_index_open", "ds2i_gpu_index_open_file", "ds2i_gpu_index_close", "ds2i_gpu_index_size",
     "ds2i_gpu_index_num_docs", "ds2i_gpu_index_device_bytes", "ds2i_gpu_index_list_sizes",
     "ds2i_gpu_wand_open", "ds2i_gpu_wand_open_file", "ds2i_gpu_wand_close",
-    "ds2i_gpu_query_batch", "ds2i_gpu_batch_prepare", "ds2i_gpu_batch_run", "ds2i_gpu_batch_fetch",
+    "ds2i_gpu_query_batch", "ds2i_gpu_batch_prepare", "ds2i_gpu_batch_run", "ds2i_gpu_batch_run_ex", "ds2i_gpu_batch_fetch",
     "ds2i_gpu_batch_stats", "ds2i_gpu_batch_device_results", "ds2i_gpu_batch_free",
     "ds2i_gpu_decode_lists", "ds2i_gpu_next_geq_batch",
 ]
@@ -51,6 +51,7 @@ def lib():
     L.ds2i_gpu_query_batch.argtypes = [vp, vp, C.c_int, C.c_uint32, u32p, u64p, C.c_size_t, u64p, f32p, f32p]
     L.ds2i_gpu_batch_prepare.argtypes = [vp, vp, u32p, u64p, C.c_size_t, C.POINTER(vp)]
     L.ds2i_gpu_batch_run.argtypes = [vp, C.c_int, C.c_uint32, f32p]
+    L.ds2i_gpu_batch_run_ex.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, f32p]
     L.ds2i_gpu_batch_fetch.argtypes = [vp, u64p, f32p]
     L.ds2i_gpu_batch_stats.argtypes = [vp, u64p]
     L.ds2i_gpu_batch_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]

@@ -141,11 +141,13 @@ class QueryBatch:
         _native.check(_native.lib().ds2i_gpu_batch_prepare(index._h, wh, _p(flat, C.c_uint32), _p(offs, C.c_uint64), self.nq, C.byref(self._h)))
         self.h2d_bytes = flat.nbytes + offs.nbytes
 
-    def run(self, op, k=10):
+    def run(self, op, k=10, faithful=False):
+        """Evaluate `op` over the resident batch; returns the CUDA-event time in ms.  faithful=True
+        selects the literal one-candidate-at-a-time kernels (DS2I_RUN_FAITHFUL)."""
         ms = C.c_float()
         self._k = k
         self._op = op
-        _native.check(_native.lib().ds2i_gpu_batch_run(self._h, OPS.index(op), k, C.byref(ms)))
+        _native.check(_native.lib().ds2i_gpu_batch_run_ex(self._h, OPS.index(op), k, 1 if faithful else 0, C.byref(ms)))
         return ms.value
 
     def fetch(self):

@@ -20,6 +20,7 @@
 
 #include "format.hpp"
 #include "query_kernels.cuh"
+#include "and_kernels.cuh"
 #include "pef_kernels.cuh"
 
 using namespace ds2i_gpu;
@@ -108,6 +109,11 @@ struct ds2i_gpu_batch {
     dev_buf<uint8_t> ord_size, ord_maxw;
     dev_buf<uint64_t> out_counts;
     dev_buf<unsigned long long> stats;
+    // block-at-a-time conjunctive path: work items = (query, chunk of blocks of its shortest list)
+    dev_buf<AndItem> and_items;
+    dev_buf<uint32_t> and_order, and_item_begin, and_item_counts, and_item_sizes;
+    dev_buf<float> and_item_scores;
+    uint32_t n_and_items = 0;
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~ds2i_gpu_batch() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
@@ -266,7 +272,7 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     std::vector<uint32_t> q_begin(nq + 1, 0), term, sched(nq);
     std::vector<float> q_weight, max_weight;
     std::vector<uint8_t> ord_size, ord_maxw;
-    std::vector<uint64_t> cost(nq, 0);
+    std::vector<uint64_t> cost(nq, 0), shortest(nq, 0);
     struct ent { uint64_t n; float mw; uint8_t pos; };
     std::vector<uint32_t> tmp;
     std::vector<ent> ents;
@@ -300,9 +306,26 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
         std::sort(by_mw.begin(), by_mw.end(), [](ent const& l, ent const& r) { return l.mw < r.mw; });
         for (auto const& e : by_size) ord_size.push_back(e.pos);
         for (auto const& e : by_mw) ord_maxw.push_back(e.pos);
+        shortest[q] = ents.empty() ? 0 : by_size[0].n;
     }
     std::iota(sched.begin(), sched.end(), 0u);
     std::stable_sort(sched.begin(), sched.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+
+    // work items of the conjunctive path
+    std::vector<AndItem> items;
+    std::vector<uint32_t> item_begin(nq + 1, 0), item_order;
+    for (size_t q = 0; q < nq; ++q) {
+        uint64_t nb0 = (shortest[q] + BLOCK - 1) / BLOCK;
+        for (uint64_t fb = 0; fb < nb0; fb += AND_CHUNK_BLOCKS) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
+        item_begin[q + 1] = uint32_t(items.size());
+    }
+    item_order.reserve(items.size());
+    for (uint32_t qi : sched)
+        for (uint32_t it = item_begin[qi]; it < item_begin[qi + 1]; ++it) item_order.push_back(it);
+    b->n_and_items = uint32_t(items.size());
+    CUDA_TRY(b->and_items.upload(items)); CUDA_TRY(b->and_order.upload(item_order)); CUDA_TRY(b->and_item_begin.upload(item_begin));
+    CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
+    CUDA_TRY(b->and_item_scores.alloc(items.size() * MAX_K));
 
     b->max_terms = max_terms;
     CUDA_TRY(b->q_begin.upload(q_begin)); CUDA_TRY(b->term.upload(term)); CUDA_TRY(b->sched.upload(sched));
@@ -335,6 +358,28 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     return DS2I_OK;
 }
 
+template <int CODEC, bool RANKED>
+static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
+    ds2i_gpu_index* ix = b->index;
+    const int warps = 4;
+    size_t smem = warps * warp_smem_bytes(b->max_terms);
+    auto kern = and_block_kernel<CODEC, RANKED>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return fail(DS2I_E_CUDA, "conjunctive kernel does not fit on an SM");
+    int grid = per_sm * ix->sm_count;
+    int needed = int((b->n_and_items + warps - 1) / warps);
+    if (grid > needed) grid = std::max(needed, 1);
+    AndJob job{b->and_items.p, b->and_order.p, b->n_and_items, b->work_counter.p, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
+    DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr};
+    if (b->n_and_items) kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, b->max_terms);
+    merge_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->and_item_begin.p, b->nq, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p,
+                                                 k, RANKED, b->out_counts.p, b->out_scores.p);
+    b->launches += 1;   // + the one the caller counts
+    return DS2I_OK;
+}
+
 template <int CODEC>
 static int launch_query_op(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32_t k) {
     switch (op) {
@@ -351,6 +396,10 @@ static int launch_query_op(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32
 }
 
 extern "C" int ds2i_gpu_batch_run(ds2i_gpu_batch* b, int op, uint32_t k, float* out_elapsed_ms) {
+    return ds2i_gpu_batch_run_ex(b, op, k, 0u, out_elapsed_ms);
+}
+
+extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint32_t flags, float* out_elapsed_ms) {
     if (!b) return fail(DS2I_E_ARG, "null batch");
     if (op < 0 || op > OP_RANKED_OR) return fail(DS2I_E_ARG, "unknown operator");
     const bool ranked = op >= OP_RANKED_AND;
@@ -369,6 +418,12 @@ extern "C" int ds2i_gpu_batch_run(ds2i_gpu_batch* b, int op, uint32_t k, float* 
     int rc = DS2I_OK;
     if (b->nq) {
         if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
+        else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND)) {
+            if (!ranked) k = 1;
+            if (ix->codec == CODEC_OPTPFOR) rc = op == OP_AND ? launch_and_block<CODEC_OPTPFOR, false>(b, db, k) : launch_and_block<CODEC_OPTPFOR, true>(b, db, k);
+            else if (ix->codec == CODEC_INTERPOLATIVE) rc = op == OP_AND ? launch_and_block<CODEC_INTERPOLATIVE, false>(b, db, k) : launch_and_block<CODEC_INTERPOLATIVE, true>(b, db, k);
+            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+        }
         else if (ix->codec == CODEC_OPTPFOR) rc = launch_query_op<CODEC_OPTPFOR>(b, db, op, k);
         else if (ix->codec == CODEC_INTERPOLATIVE) rc = launch_query_op<CODEC_INTERPOLATIVE>(b, db, op, k);
         else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
