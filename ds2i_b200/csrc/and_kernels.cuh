@@ -76,7 +76,7 @@ __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* d, uint32_t x
 template <int CODEC, bool RANKED>
 __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t s16tab[16];
+    __shared__ uint32_t s16tab[S16_TAB_WORDS];
     s16_table_init(s16tab);
     __syncthreads();
 

@@ -125,16 +125,22 @@ struct BlockEnum {
     }
 
     // block_posting_list.hpp:292-319
-    static __device__ __forceinline__ void decode_docs_block(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b) {
+    static __device__ __noinline__ void decode_docs_block(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b) {
         const unsigned lane = lane_id();
         const uint32_t nblocks = st->nblocks, n = st->n;
         const uint8_t* maxs = idx.lists + st->maxs_off;
         const uint8_t* ends = maxs + 4ull * nblocks;
+        // lanes 0..3 fetch endpoint[b-1], endpoint[b], max[b-1], max[b] with one converged load each
         uint32_t v = 0;
-        if (lane == 0) v = b ? ldg_u32_unaligned(ends + 4ull * (b - 1)) : 0u;
-        else if (lane == 1) v = (b + 1 < nblocks) ? ldg_u32_unaligned(ends + 4ull * b) : st->data_bytes;
-        else if (lane == 2) v = b ? ldg_u32_unaligned(maxs + 4ull * (b - 1)) : 0xffffffffu;
-        else if (lane == 3) v = ldg_u32_unaligned(maxs + 4ull * b);
+        {
+            const bool is_end = lane < 2;
+            const uint32_t which = lane & 1u;                       // 0: entry b-1, 1: entry b
+            const bool have = lane < 4 && (which ? (is_end ? (b + 1 < nblocks) : true) : (b != 0));
+            const uint8_t* p = (is_end ? ends : maxs) + 4ull * (b + which) - 4ull;
+            if (have) v = ldg_u32_unaligned(p);
+            else if (lane == 1) v = st->data_bytes;
+            else if (lane == 2) v = 0xffffffffu;
+        }
         const uint32_t e0 = __shfl_sync(FULL, v, 0), e1 = __shfl_sync(FULL, v, 1);
         const uint32_t cur_base = __shfl_sync(FULL, v, 2) + 1u;
         const uint32_t cur_max = __shfl_sync(FULL, v, 3);

@@ -26,20 +26,30 @@ __device__ __constant__ uint32_t c_s16_layout[16] = {
     S16(4, 7, 0, 0, 0, 0),  S16(1, 10, 2, 9, 0, 0), S16(2, 14, 0, 0, 0, 0), S16(1, 28, 0, 0, 0, 0)};
 #undef S16
 
-__device__ __forceinline__ void s16_table_init(uint32_t* tab /* 16 words of shared memory */) {
-    if (threadIdx.x < 16) tab[threadIdx.x] = c_s16_layout[threadIdx.x];
-}
+// Per-CTA lookup tables in shared memory: tab[0..15] = values per selector, tab[16 + sel*28 + j] =
+// (shift | width << 8) of the j-th value of a word with that selector.
+constexpr uint32_t S16_TAB_WORDS = 16 + 16 * 28;
+
 __device__ __forceinline__ uint32_t s16_count(uint32_t lay) {
     return (lay & 31u) + ((lay >> 10) & 31u) + ((lay >> 20) & 31u);
 }
-// j-th value of a Simple16 word
-__device__ __forceinline__ uint32_t s16_value(uint32_t word, uint32_t lay, uint32_t j) {
-    uint32_t n1 = lay & 31u, b1 = (lay >> 5) & 31u, n2 = (lay >> 10) & 31u, b2 = (lay >> 15) & 31u, b3 = lay >> 25;
-    uint32_t off, w;
-    if (j < n1) { off = j * b1; w = b1; }
-    else if (j < n1 + n2) { off = n1 * b1 + (j - n1) * b2; w = b2; }
-    else { off = n1 * b1 + n2 * b2 + (j - n1 - n2) * b3; w = b3; }
-    return (word >> (28u - off - w)) & ((1u << w) - 1u);
+__device__ __forceinline__ void s16_table_init(uint32_t* tab /* S16_TAB_WORDS words of shared memory */) {
+    for (uint32_t t = threadIdx.x; t < S16_TAB_WORDS; t += blockDim.x) {
+        if (t < 16) { tab[t] = s16_count(c_s16_layout[t]); continue; }
+        uint32_t sel = (t - 16) / 28, j = (t - 16) % 28;
+        uint32_t lay = c_s16_layout[sel];
+        uint32_t n1 = lay & 31u, b1 = (lay >> 5) & 31u, n2 = (lay >> 10) & 31u, b2 = (lay >> 15) & 31u, n3 = (lay >> 20) & 31u, b3 = lay >> 25;
+        uint32_t off = 0, w = 0;
+        if (j < n1) { off = j * b1; w = b1; }
+        else if (j < n1 + n2) { off = n1 * b1 + (j - n1) * b2; w = b2; }
+        else if (j < n1 + n2 + n3) { off = n1 * b1 + n2 * b2 + (j - n1 - n2) * b3; w = b3; }
+        tab[t] = w ? ((28u - off - w) | (w << 8)) : 0u;
+    }
+}
+// j-th value of a Simple16 word (values fill the 28 payload bits MSB-first)
+__device__ __forceinline__ uint32_t s16_value(const uint32_t* tab, uint32_t word, uint32_t j) {
+    uint32_t t = tab[16u + (word >> 28) * 28u + j];
+    return (word >> (t & 31u)) & ((1u << (t >> 8)) - 1u);
 }
 
 // ---- TightVariableByte, one value (block_codecs.hpp:84-98); single-lane helper -----------------
@@ -58,8 +68,11 @@ __device__ __forceinline__ uint32_t vbyte_decode(const uint32_t* win, uint32_t& 
 // Header word b<<26 | nExc<<16 | excWords; Simple16 exception stream; 4 groups of 32 values packed
 // LSB-first at b bits (bitpackinghelpers.h fastunpack).  Lane l unpacks element l of each group;
 // the byte phase of the (unaligned) block is folded into the bit position, so no realignment pass.
-__device__ __forceinline__ uint32_t decode_optpfor128(const uint32_t* win, uint32_t off, uint32_t* out,
-                                                      uint32_t* scratch, const uint32_t* s16tab) {
+// Exceptions: the Simple16 words sit one per lane; every lane locates the word holding "its" two
+// values (position gap e and high bits nExc+e) with a 5-step shuffle search over the scanned
+// per-word counts and extracts them with one table lookup each — no per-word expansion loop.
+__device__ __noinline__ uint32_t decode_optpfor128(const uint32_t* win, uint32_t off, uint32_t* out,
+                                                   uint32_t* scratch, const uint32_t* s16tab) {
     const unsigned lane = lane_id();
     const uint32_t w0 = lds_u32(win, off);
     const uint32_t b = w0 >> 26;
@@ -76,34 +89,62 @@ __device__ __forceinline__ uint32_t decode_optpfor128(const uint32_t* win, uint3
     for (uint32_t j = 0; j < 4; ++j) out[32 * j + lane] = lds_bits(win, pbit + 32u * b * j, b);
 
     if (nexc) {
-        // Simple16: lane per word, warp scan of the per-word counts, each lane expands its word.
-        uint32_t* E = scratch;
-        const uint32_t need = 2u * nexc;
-        uint32_t produced = 0;
-        for (uint32_t base = 0; base < excw && produced < need; base += 32) {
-            uint32_t w = base + lane;
-            bool valid = w < excw;
-            uint32_t word = valid ? lds_u32(win, off + 4u * (1u + w)) : 0u;
-            uint32_t lay = s16tab[word >> 28];
-            uint32_t cnt = valid ? s16_count(lay) : 0u;
-            uint32_t incl = warp_inclusive_scan(cnt);
-            uint32_t start = produced + incl - cnt;
-            for (uint32_t j = 0; j < cnt; ++j) {
-                uint32_t idx = start + j;
-                if (idx < SCRATCH_WORDS) E[idx] = s16_value(word, lay, j);
+        if (excw <= 32) {
+            const uint32_t word = lane < excw ? lds_u32(win, off + 4u * (1u + lane)) : 0u;
+            const uint32_t cnt = lane < excw ? s16tab[word >> 28] : 0u;
+            const uint32_t start = warp_inclusive_scan(cnt) - cnt;     // index of this word's first value
+            auto fetch = [&](uint32_t e) -> uint32_t {
+                uint32_t w = 0;
+#pragma unroll
+                for (uint32_t s = 16; s >= 1; s >>= 1) {
+                    uint32_t st = __shfl_sync(FULL, start, (w + s) & 31u);
+                    if (st <= e) w += s;
+                }
+                uint32_t wv = __shfl_sync(FULL, word, w);
+                uint32_t sv = __shfl_sync(FULL, start, w);
+                uint32_t j = e - sv;
+                return s16_value(s16tab, wv, j < 28u ? j : 0u);
+            };
+            __syncwarp();
+            uint32_t carry = 0;
+            for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
+                uint32_t e = e0 + lane;
+                bool valid = e < nexc;
+                uint32_t g = fetch(valid ? e : 0u) + 1u;
+                uint32_t hi = fetch(valid ? nexc + e : 0u) + 1u;
+                uint32_t incl = warp_inclusive_scan(valid ? g : 0u);
+                uint32_t p = carry + incl - 1u;
+                if (valid && p < BLOCK) out[p] |= hi << b;
+                carry += __shfl_sync(FULL, incl, 31);
             }
-            produced += __shfl_sync(FULL, incl, 31);
-        }
-        __syncwarp();
-        // exceptions: first half = position gaps - 1 (first absolute), second half = high bits - 1
-        uint32_t carry = 0;
-        for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
-            uint32_t e = e0 + lane;
-            uint32_t g = e < nexc ? E[e] + 1u : 0u;
-            uint32_t incl = warp_inclusive_scan(g);
-            uint32_t p = carry + incl - 1u;
-            if (e < nexc && p < BLOCK) out[p] |= (E[nexc + e] + 1u) << b;
-            carry += __shfl_sync(FULL, incl, 31);
+        } else {
+            // long exception streams (> 32 Simple16 words): expand through shared memory
+            uint32_t* E = scratch;
+            const uint32_t need = 2u * nexc;
+            uint32_t produced = 0;
+            for (uint32_t base = 0; base < excw && produced < need; base += 32) {
+                uint32_t w = base + lane;
+                bool valid = w < excw;
+                uint32_t word = valid ? lds_u32(win, off + 4u * (1u + w)) : 0u;
+                uint32_t cnt = valid ? s16tab[word >> 28] : 0u;
+                uint32_t incl = warp_inclusive_scan(cnt);
+                uint32_t start = produced + incl - cnt;
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    uint32_t idx = start + j;
+                    if (idx < SCRATCH_WORDS) E[idx] = s16_value(s16tab, word, j);
+                }
+                produced += __shfl_sync(FULL, incl, 31);
+            }
+            __syncwarp();
+            uint32_t carry = 0;
+            for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
+                uint32_t e = e0 + lane;
+                uint32_t g = e < nexc ? E[e] + 1u : 0u;
+                uint32_t incl = warp_inclusive_scan(g);
+                uint32_t p = carry + incl - 1u;
+                if (e < nexc && p < BLOCK) out[p] |= (E[nexc + e] + 1u) << b;
+                carry += __shfl_sync(FULL, incl, 31);
+            }
         }
     }
     __syncwarp();
@@ -114,7 +155,7 @@ __device__ __forceinline__ uint32_t decode_optpfor128(const uint32_t* win, uint3
 // Bit-serial: each code length depends on previously decoded values, so lane 0 decodes while the
 // warp waits.  Writes the PREFIX SUMS P[0..n-1] (P[n-1] = sum) into out; callers turn them into
 // docids (base + P[i] + i) or freqs (P[i] - P[i-1]) in parallel.
-__device__ __forceinline__ uint32_t decode_interpolative_prefix(const uint32_t* win, uint32_t off, uint32_t n,
+__device__ __noinline__ uint32_t decode_interpolative_prefix(const uint32_t* win, uint32_t off, uint32_t n,
                                                                 uint32_t sum_of_values, uint32_t* out,
                                                                 uint32_t* scratch) {
     uint32_t consumed = 0;

@@ -495,7 +495,7 @@ struct DecodeJob {
 template <int CODEC>
 __global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, DecodeJob job) {
     __shared__ __align__(16) uint8_t smem_raw[8 * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16)];
-    __shared__ uint32_t s16tab[16];
+    __shared__ uint32_t s16tab[S16_TAB_WORDS];
     s16_table_init(s16tab);
     __syncthreads();
     typedef BlockEnum<CODEC> E;
@@ -604,7 +604,7 @@ struct GeqJob {
 template <int CODEC>
 __global__ void __launch_bounds__(128) next_geq_kernel(DevIndex idx, GeqJob job) {
     __shared__ __align__(16) uint8_t smem_raw[4 * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16)];
-    __shared__ uint32_t s16tab[16];
+    __shared__ uint32_t s16tab[S16_TAB_WORDS];
     s16_table_init(s16tab);
     __syncthreads();
     typedef BlockEnum<CODEC> E;

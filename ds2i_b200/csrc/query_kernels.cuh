@@ -84,7 +84,7 @@ __host__ __device__ constexpr size_t warp_smem_bytes(int slots) {
 template <int CODEC, int OP>
 __global__ void __launch_bounds__(128) query_kernel(DevIndex idx, DevWand wand, DevBatch batch, uint32_t k, int slots) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t s16tab[16];
+    __shared__ uint32_t s16tab[S16_TAB_WORDS];
     s16_table_init(s16tab);
     __syncthreads();
 
