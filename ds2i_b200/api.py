@@ -190,10 +190,19 @@ class QueryBatch:
             pass
 
 
+def flatten_queries(queries):
+    """list of term-id lists -> (terms u32[], offsets u64[nq+1]): the host buffers of the C ABI."""
+    return _flatten(queries)
+
+
 def query_batch(index, wdata, op, queries, k=10):
-    """One call, host buffers in and out (ds2i_gpu_query_batch).  Returns (counts, scores, elapsed_ms)."""
-    flat, offs = _flatten(queries)
-    nq = len(queries)
+    """One call, host buffers in and out (ds2i_gpu_query_batch).  `queries` is a list of term-id
+    lists or the (terms, offsets) pair of flatten_queries.  Returns (counts, scores, elapsed_ms)."""
+    if isinstance(queries, tuple):
+        flat, offs = queries
+    else:
+        flat, offs = _flatten(queries)
+    nq = len(offs) - 1
     counts = np.zeros(max(nq, 1), dtype=np.uint64)
     scores = np.zeros((max(nq, 1), k), dtype=np.float32)
     ms = C.c_float()

@@ -16,6 +16,7 @@
 namespace ds2i_gpu {
 
 constexpr uint32_t AND_CHUNK_BLOCKS = 32;     // blocks of the shortest list per work item
+constexpr int AND_SMALL_TERMS = 0;            // queries up to this many terms run in the high-occupancy launch
 
 struct AndItem { uint32_t query, first_block; };
 
@@ -29,16 +30,38 @@ struct AndJob {
     float* item_scores;        // nitems * k
 };
 
-// first block index in [lo, nblocks) whose block_max >= bound (exists: bound <= last max).
-// 32 consecutive entries first (the common short skip), then a 32-ary search of the rest.
-__device__ __forceinline__ uint32_t find_block(WarpCtx& c, const uint8_t* maxs, uint32_t lo, uint32_t nblocks, uint32_t bound) {
+// first block index in [lo, nblocks) whose block_max >= bound (exists: bound <= last max), together
+// with that block's metadata.  The first probe reads 32 consecutive block_max entries AND the
+// matching block_endpoints in the same step, so in the common short-skip case the block's byte range
+// and base arrive with the probe (one memory round trip instead of two); longer skips finish with a
+// 32-ary search and a separate metadata fetch.
+struct BlockMeta { uint32_t block, e0, e1, prev_max, cur_max; bool have; };
+
+__device__ __forceinline__ BlockMeta find_block(WarpCtx& c, const ListState* s, const uint8_t* maxs, uint32_t lo, uint32_t lo_prev_max, uint32_t bound) {
     const unsigned lane = lane_id();
+    const uint32_t nblocks = s->nblocks;
+    const uint8_t* ends = maxs + 4ull * nblocks;
+    BlockMeta r;
     {
         uint32_t bi = lo + lane;
         uint32_t m = bi < nblocks ? ldg_u32_unaligned(maxs + 4ull * bi) : 0xffffffffu;
+        uint32_t e = (bi < nblocks && bi) ? ldg_u32_unaligned(ends + 4ull * bi - 4ull) : 0u;    // start of block bi
         unsigned hit = __ballot_sync(FULL, m >= bound);
         c.c_maxs += 32;
-        if (hit) return lo + (__ffs(hit) - 1);
+        if (hit) {
+            uint32_t f = __ffs(hit) - 1;
+            r.block = lo + f;
+            r.cur_max = __shfl_sync(FULL, m, f);
+            r.e0 = __shfl_sync(FULL, e, f);
+            uint32_t pm = __shfl_sync(FULL, m, (f + 31) & 31);
+            r.prev_max = f ? pm : lo_prev_max;
+            uint32_t en = __shfl_sync(FULL, e, (f + 1) & 31);
+            r.have = true;
+            if (r.block + 1 >= nblocks) r.e1 = s->data_bytes;
+            else if (f < 31) r.e1 = en;
+            else r.have = false;          // end offset not among the 32 probed entries
+            return r;
+        }
         lo += 32;
     }
     uint32_t hi = nblocks - 1;          // invariant: max[hi] >= bound, every block < lo has max < bound
@@ -61,7 +84,9 @@ __device__ __forceinline__ uint32_t find_block(WarpCtx& c, const uint8_t* maxs, 
     uint32_t m = bi <= hi ? ldg_u32_unaligned(maxs + 4ull * bi) : 0xffffffffu;
     unsigned hit = __ballot_sync(FULL, m >= bound);
     c.c_maxs += hi - lo + 1;
-    return lo + (__ffs(hit) - 1);
+    r.block = lo + (__ffs(hit) - 1);
+    r.have = false; r.e0 = r.e1 = r.prev_max = r.cur_max = 0;
+    return r;
 }
 
 // position of the first element >= x in a sorted 128-entry block (padded with 0xffffffff)
@@ -75,22 +100,20 @@ __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* d, uint32_t x
 
 template <int CODEC, bool RANKED>
 __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t s16tab[S16_TAB_WORDS];
-    s16_table_init(s16tab);
+    s16_table_init(smem_words(0));
     __syncthreads();
 
     typedef BlockEnum<CODEC> E;
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    uint8_t* base = smem_raw + warp * warp_smem_bytes(slots);
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes(slots);
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
     ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
     uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState));
     uint32_t* scratch = stage + STAGE_WORDS;
 
     WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar, s16tab);
+    ctx_init(c, stage, scratch, &ws->bar);
 
     while (true) {
         uint32_t ii = 0;
@@ -125,9 +148,29 @@ __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wa
 
         const uint32_t nb0 = st[0].nblocks;
         const uint32_t b_end = min(nb0, item.first_block + AND_CHUNK_BLOCKS);
+        // metadata of the whole chunk of the driving list, one block per lane, fetched in one round trip
+        uint32_t m_max = 0, m_start = 0, m_end = 0, m_first_prev;
+        {
+            static_assert(AND_CHUNK_BLOCKS <= 32, "one lane per block of the chunk");
+            const uint8_t* maxs0 = idx.lists + st[0].maxs_off;
+            const uint8_t* ends0 = maxs0 + 4ull * nb0;
+            uint32_t bi = item.first_block + lane;
+            if (bi < b_end) {
+                m_max = ldg_u32_unaligned(maxs0 + 4ull * bi);
+                m_start = bi ? ldg_u32_unaligned(ends0 + 4ull * bi - 4ull) : 0u;
+                m_end = bi + 1 < nb0 ? ldg_u32_unaligned(ends0 + 4ull * bi) : st[0].data_bytes;
+            }
+            uint32_t pm = (lane == 0 && item.first_block) ? ldg_u32_unaligned(maxs0 + 4ull * item.first_block - 4ull) : 0xffffffffu;
+            m_first_prev = __shfl_sync(FULL, pm, 0);
+        }
         bool exhausted = false;
         for (uint32_t b0 = item.first_block; b0 < b_end && !exhausted; ++b0) {
-            E::decode_docs_block(c, idx, &st[0], b0);
+            {
+                uint32_t l = b0 - item.first_block;
+                uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31);
+                E::decode_docs_block_meta(c, idx, &st[0], b0, __shfl_sync(FULL, m_start, l), __shfl_sync(FULL, m_end, l),
+                                          l ? pm : m_first_prev, __shfl_sync(FULL, m_max, l));
+            }
             if (b0 + 1 < nb0) prefetch_l2(idx.lists + st[0].data_off + st[0].block_end + lane * 32u);   // next block of the driving list
             uint4 cv = reinterpret_cast<const uint4*>(st[0].docs)[lane];
             uint32_t cand[4] = {cv.x, cv.y, cv.z, cv.w};
@@ -155,8 +198,10 @@ __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wa
                     }
                     uint32_t cur_block = s->cur_block;
                     if (cur_block == 0xffffffffu || cmin > s->cur_max) {
-                        uint32_t nb = find_block(c, maxs, cur_block == 0xffffffffu ? 0u : cur_block + 1, s->nblocks, cmin);
-                        E::decode_docs_block(c, idx, s, nb);
+                        bool fresh = cur_block == 0xffffffffu;
+                        BlockMeta bm = find_block(c, s, maxs, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max, cmin);
+                        if (bm.have) E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+                        else E::decode_docs_block(c, idx, s, bm.block);
                     }
                     const uint32_t cur_max = s->cur_max;
                     const uint32_t* d = s->docs;

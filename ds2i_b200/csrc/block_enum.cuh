@@ -42,7 +42,6 @@ struct WarpCtx {
     uint32_t* stage;        // STAGE_WORDS
     uint32_t* scratch;      // SCRATCH_WORDS
     uint64_t* bar;
-    const uint32_t* s16tab;
     uint32_t phase;
     uint64_t win_start;     // absolute byte range currently staged
     uint32_t win_bytes;
@@ -50,9 +49,8 @@ struct WarpCtx {
     uint32_t c_docs_blocks, c_freqs_blocks, c_docs_bytes, c_freqs_bytes, c_maxs, c_scored;
 };
 
-__device__ __forceinline__ void ctx_init(WarpCtx& c, uint32_t* stage, uint32_t* scratch, uint64_t* bar,
-                                         const uint32_t* s16tab) {
-    c.stage = stage; c.scratch = scratch; c.bar = bar; c.s16tab = s16tab;
+__device__ __forceinline__ void ctx_init(WarpCtx& c, uint32_t* stage, uint32_t* scratch, uint64_t* bar) {
+    c.stage = stage; c.scratch = scratch; c.bar = bar;
     c.phase = 0; c.win_start = 0; c.win_bytes = 0;
     c.c_docs_blocks = c.c_freqs_blocks = c.c_docs_bytes = c.c_freqs_bytes = c.c_maxs = c.c_scored = 0;
     if (lane_id() == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -102,11 +100,11 @@ __device__ __forceinline__ uint32_t decode_values(WarpCtx& c, uint32_t off, uint
                                                   uint32_t* buf, bool& prefix_out) {
     if (CODEC != CODEC_INTERPOLATIVE && size == BLOCK) {
         prefix_out = false;
-        if (CODEC == CODEC_OPTPFOR) return decode_optpfor128(c.stage, off, buf, c.scratch, c.s16tab);
+        if (CODEC == CODEC_OPTPFOR) return decode_optpfor128(smem_offset(c.stage), off, smem_offset(buf), smem_offset(c.scratch));
     }
     // n < block_size => every codec falls back to interpolative (block_codecs.hpp:196-199,215-217)
     prefix_out = true;
-    return decode_interpolative_prefix(c.stage, off, size, sum_of_values, buf, c.scratch);
+    return decode_interpolative_prefix(smem_offset(c.stage), off, size, sum_of_values, smem_offset(buf), smem_offset(c.scratch));
 }
 
 template <int CODEC>
@@ -125,9 +123,9 @@ struct BlockEnum {
     }
 
     // block_posting_list.hpp:292-319
-    static __device__ __noinline__ void decode_docs_block(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b) {
+    static __device__ __forceinline__ void decode_docs_block(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b) {
         const unsigned lane = lane_id();
-        const uint32_t nblocks = st->nblocks, n = st->n;
+        const uint32_t nblocks = st->nblocks;
         const uint8_t* maxs = idx.lists + st->maxs_off;
         const uint8_t* ends = maxs + 4ull * nblocks;
         // lanes 0..3 fetch endpoint[b-1], endpoint[b], max[b-1], max[b] with one converged load each
@@ -142,8 +140,18 @@ struct BlockEnum {
             else if (lane == 2) v = 0xffffffffu;
         }
         const uint32_t e0 = __shfl_sync(FULL, v, 0), e1 = __shfl_sync(FULL, v, 1);
-        const uint32_t cur_base = __shfl_sync(FULL, v, 2) + 1u;
+        const uint32_t prev_max = __shfl_sync(FULL, v, 2);
         const uint32_t cur_max = __shfl_sync(FULL, v, 3);
+        decode_docs_block_meta(c, idx, st, b, e0, e1, prev_max, cur_max);
+    }
+
+    // the same with the block's metadata already in hand: e0/e1 = byte range of the block inside the
+    // list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
+    static __device__ __forceinline__ void decode_docs_block_meta(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b,
+                                                                  uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
+        const unsigned lane = lane_id();
+        const uint32_t n = st->n;
+        const uint32_t cur_base = prev_max + 1u;
         const uint32_t size = ((b + 1) * BLOCK <= n) ? BLOCK : (n % BLOCK);
         const uint64_t data_off = st->data_off;
 

@@ -29,6 +29,7 @@ __device__ __constant__ uint32_t c_s16_layout[16] = {
 // Per-CTA lookup tables in shared memory: tab[0..15] = values per selector, tab[16 + sel*28 + j] =
 // (shift | width << 8) of the j-th value of a word with that selector.
 constexpr uint32_t S16_TAB_WORDS = 16 + 16 * 28;
+constexpr uint32_t S16_TAB_BYTES = S16_TAB_WORDS * 4;     // sits at offset 0 of g_smem in every kernel
 
 __device__ __forceinline__ uint32_t s16_count(uint32_t lay) {
     return (lay & 31u) + ((lay >> 10) & 31u) + ((lay >> 20) & 31u);
@@ -71,8 +72,11 @@ __device__ __forceinline__ uint32_t vbyte_decode(const uint32_t* win, uint32_t& 
 // Exceptions: the Simple16 words sit one per lane; every lane locates the word holding "its" two
 // values (position gap e and high bits nExc+e) with a 5-step shuffle search over the scanned
 // per-word counts and extracts them with one table lookup each — no per-word expansion loop.
-__device__ __noinline__ uint32_t decode_optpfor128(const uint32_t* win, uint32_t off, uint32_t* out,
-                                                   uint32_t* scratch, const uint32_t* s16tab) {
+__device__ __noinline__ uint32_t decode_optpfor128(uint32_t win_off, uint32_t off, uint32_t out_off, uint32_t scratch_off) {
+    const uint32_t* win = smem_words(win_off);
+    uint32_t* out = smem_words(out_off);
+    uint32_t* scratch = smem_words(scratch_off);
+    const uint32_t* s16tab = smem_words(0);
     const unsigned lane = lane_id();
     const uint32_t w0 = lds_u32(win, off);
     const uint32_t b = w0 >> 26;
@@ -93,10 +97,10 @@ __device__ __noinline__ uint32_t decode_optpfor128(const uint32_t* win, uint32_t
             const uint32_t word = lane < excw ? lds_u32(win, off + 4u * (1u + lane)) : 0u;
             const uint32_t cnt = lane < excw ? s16tab[word >> 28] : 0u;
             const uint32_t start = warp_inclusive_scan(cnt) - cnt;     // index of this word's first value
+            const uint32_t s_hi = excw > 1 ? 1u << (31 - __clz(excw - 1)) : 0u;   // search steps follow the word count
             auto fetch = [&](uint32_t e) -> uint32_t {
                 uint32_t w = 0;
-#pragma unroll
-                for (uint32_t s = 16; s >= 1; s >>= 1) {
+                for (uint32_t s = s_hi; s >= 1; s >>= 1) {
                     uint32_t st = __shfl_sync(FULL, start, (w + s) & 31u);
                     if (st <= e) w += s;
                 }
@@ -155,9 +159,11 @@ __device__ __noinline__ uint32_t decode_optpfor128(const uint32_t* win, uint32_t
 // Bit-serial: each code length depends on previously decoded values, so lane 0 decodes while the
 // warp waits.  Writes the PREFIX SUMS P[0..n-1] (P[n-1] = sum) into out; callers turn them into
 // docids (base + P[i] + i) or freqs (P[i] - P[i-1]) in parallel.
-__device__ __noinline__ uint32_t decode_interpolative_prefix(const uint32_t* win, uint32_t off, uint32_t n,
-                                                                uint32_t sum_of_values, uint32_t* out,
-                                                                uint32_t* scratch) {
+__device__ __noinline__ uint32_t decode_interpolative_prefix(uint32_t win_off, uint32_t off, uint32_t n,
+                                                             uint32_t sum_of_values, uint32_t out_off, uint32_t scratch_off) {
+    const uint32_t* win = smem_words(win_off);
+    uint32_t* out = smem_words(out_off);
+    uint32_t* scratch = smem_words(scratch_off);
     uint32_t consumed = 0;
     if (lane_id() == 0) {
         uint32_t pos = off;

@@ -8,6 +8,15 @@ namespace ds2i_gpu {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// The one dynamic shared-memory window of every kernel in this library.  De-inlined device
+// functions address it by byte offset, so the compiler keeps emitting LDS/STS (a generic pointer
+// parameter would turn every access into a generic LD/ST).
+extern __shared__ __align__(16) uint8_t g_smem[];
+__device__ __forceinline__ uint32_t* smem_words(uint32_t byte_off) { return reinterpret_cast<uint32_t*>(g_smem + byte_off); }
+__device__ __forceinline__ uint32_t smem_offset(const void* p) {
+    return uint32_t(reinterpret_cast<const uint8_t*>(p) - g_smem);
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {

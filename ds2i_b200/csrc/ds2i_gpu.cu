@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <memory>
 #include <numeric>
 #include <string>
@@ -113,7 +115,7 @@ struct ds2i_gpu_batch {
     dev_buf<AndItem> and_items;
     dev_buf<uint32_t> and_order, and_item_begin, and_item_counts, and_item_sizes;
     dev_buf<float> and_item_scores;
-    uint32_t n_and_items = 0;
+    uint32_t n_and_items = 0, n_and_items_large = 0;
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~ds2i_gpu_batch() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
@@ -319,9 +321,17 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
         for (uint64_t fb = 0; fb < nb0; fb += AND_CHUNK_BLOCKS) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
         item_begin[q + 1] = uint32_t(items.size());
     }
+    // two occupancy classes: queries with few terms run with small per-warp shared memory (more
+    // resident warps); within a class the items of the costliest queries come first
     item_order.reserve(items.size());
-    for (uint32_t qi : sched)
-        for (uint32_t it = item_begin[qi]; it < item_begin[qi + 1]; ++it) item_order.push_back(it);
+    for (int cls = 0; cls < 2; ++cls) {
+        for (uint32_t qi : sched) {
+            bool small = (q_begin[qi + 1] - q_begin[qi]) <= uint32_t(AND_SMALL_TERMS);
+            if (small != (cls == 1)) continue;
+            for (uint32_t it = item_begin[qi]; it < item_begin[qi + 1]; ++it) item_order.push_back(it);
+        }
+        if (cls == 0) b->n_and_items_large = uint32_t(item_order.size());
+    }
     b->n_and_items = uint32_t(items.size());
     CUDA_TRY(b->and_items.upload(items)); CUDA_TRY(b->and_order.upload(item_order)); CUDA_TRY(b->and_item_begin.upload(item_begin));
     CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
@@ -331,7 +341,7 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     CUDA_TRY(b->q_begin.upload(q_begin)); CUDA_TRY(b->term.upload(term)); CUDA_TRY(b->sched.upload(sched));
     CUDA_TRY(b->q_weight.upload(q_weight)); CUDA_TRY(b->max_weight.upload(max_weight));
     CUDA_TRY(b->ord_size.upload(ord_size)); CUDA_TRY(b->ord_maxw.upload(ord_maxw));
-    CUDA_TRY(b->work_counter.alloc(1));
+    CUDA_TRY(b->work_counter.alloc(4));
     CUDA_TRY(b->out_counts.alloc(nq)); CUDA_TRY(b->out_scores.alloc(nq * MAX_K));
     CUDA_TRY(b->stats.alloc(8));
     CUDA_TRY(cudaMemset(b->stats.p, 0, 8 * sizeof(unsigned long long)));
@@ -344,7 +354,7 @@ template <int CODEC, int OP>
 static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    size_t smem = warps * warp_smem_bytes(b->max_terms);
+    size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(b->max_terms);
     auto kern = query_kernel<CODEC, OP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
@@ -362,22 +372,29 @@ template <int CODEC, bool RANKED>
 static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    size_t smem = warps * warp_smem_bytes(b->max_terms);
     auto kern = and_block_kernel<CODEC, RANKED>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    if (per_sm < 1) return fail(DS2I_E_CUDA, "conjunctive kernel does not fit on an SM");
-    int grid = per_sm * ix->sm_count;
-    int needed = int((b->n_and_items + warps - 1) / warps);
-    if (grid > needed) grid = std::max(needed, 1);
-    AndJob job{b->and_items.p, b->and_order.p, b->n_and_items, b->work_counter.p, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
     DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr};
-    if (b->n_and_items) kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, b->max_terms);
+    // class 0: queries with many terms (slots = the batch maximum); class 1: <= AND_SMALL_TERMS terms
+    for (int cls = 0; cls < 2; ++cls) {
+        uint32_t first = cls == 0 ? 0 : b->n_and_items_large;
+        uint32_t count = cls == 0 ? b->n_and_items_large : b->n_and_items - b->n_and_items_large;
+        if (!count) continue;
+        int slots = cls == 0 ? b->max_terms : std::min(b->max_terms, AND_SMALL_TERMS);
+        size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(slots);
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S16_TAB_BYTES + warps * warp_smem_bytes(MAX_TERMS))));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+        if (per_sm < 1) return fail(DS2I_E_CUDA, "conjunctive kernel does not fit on an SM");
+        int grid = per_sm * ix->sm_count;
+        int needed = int((count + warps - 1) / warps);
+        if (grid > needed) grid = std::max(needed, 1);
+        AndJob job{b->and_items.p, b->and_order.p + first, count, b->work_counter.p + 1 + cls, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
+        kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, slots);
+        b->launches += 1;
+    }
     merge_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->and_item_begin.p, b->nq, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p,
                                                  k, RANKED, b->out_counts.p, b->out_scores.p);
-    b->launches += 1;   // + the one the caller counts
-    return DS2I_OK;
+    return DS2I_OK;   // the caller counts the merge launch
 }
 
 template <int CODEC>
@@ -413,7 +430,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     db.sched = b->sched.p; db.work_counter = b->work_counter.p; db.out_counts = b->out_counts.p;
     db.out_scores = b->out_scores.p; db.stats = b->stats.p;
     CUDA_TRY(cudaMemsetAsync(b->stats.p, 0, 8 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, 4 * sizeof(uint32_t)));
     CUDA_TRY(cudaEventRecord(b->ev0));
     int rc = DS2I_OK;
     if (b->nq) {
@@ -468,20 +485,35 @@ extern "C" int ds2i_gpu_batch_device_results(ds2i_gpu_batch* b, void** d_counts,
 
 extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { delete b; }
 
+static double now_ms() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int op, uint32_t k,
                                     const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
                                     uint64_t* out_counts, float* out_scores, float* out_elapsed_ms) {
+    static const bool trace = getenv("DS2I_GPU_TRACE") != nullptr;
+    double t0 = now_ms();
     ds2i_gpu_batch* b = nullptr;
     int rc = ds2i_gpu_batch_prepare(ix, wand, terms, query_offsets, nq, &b);
     if (rc != DS2I_OK) return rc;
     std::unique_ptr<ds2i_gpu_batch> guard(b);
+    double t1 = now_ms();
     rc = ds2i_gpu_batch_run(b, op, k, out_elapsed_ms);
     if (rc != DS2I_OK) return rc;
-    return ds2i_gpu_batch_fetch(b, out_counts, out_scores);
+    double t2 = now_ms();
+    rc = ds2i_gpu_batch_fetch(b, out_counts, out_scores);
+    double t3 = now_ms();
+    guard.reset();
+    if (trace) fprintf(stderr, "[ds2i_gpu] query_batch nq=%zu prepare %.2f ms, run %.2f ms, fetch %.2f ms, free %.2f ms\n", nq, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Batched block decode (BASELINE config 2): one warp per 128-posting block, any list, any order.
+constexpr size_t SINGLE_LIST_WARP_BYTES = sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16;
+
 struct DecodeJob {
     const uint32_t* terms;        // nterms
     const uint64_t* blk_prefix;   // nterms+1: blocks before list i
@@ -494,19 +526,17 @@ struct DecodeJob {
 
 template <int CODEC>
 __global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, DecodeJob job) {
-    __shared__ __align__(16) uint8_t smem_raw[8 * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16)];
-    __shared__ uint32_t s16tab[S16_TAB_WORDS];
-    s16_table_init(s16tab);
+    s16_table_init(smem_words(0));
     __syncthreads();
     typedef BlockEnum<CODEC> E;
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* base = smem_raw + warp * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16);
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * SINGLE_LIST_WARP_BYTES;
     ListState* st = reinterpret_cast<ListState*>(base);
     uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(ListState));
     uint32_t* scratch = stage + STAGE_WORDS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
     WarpCtx c;
-    ctx_init(c, stage, scratch, bar, s16tab);
+    ctx_init(c, stage, scratch, bar);
 
     const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
     for (uint64_t g = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp; g < job.total_blocks; g += nwarps) {
@@ -571,8 +601,8 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
             uint64_t want = (blk[nterms] + 7) / 8;
             int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
-            if (ix->codec == CODEC_OPTPFOR) decode_blocks_kernel<CODEC_OPTPFOR><<<grid, 256>>>(ix->dev, job);
-            else if (ix->codec == CODEC_INTERPOLATIVE) decode_blocks_kernel<CODEC_INTERPOLATIVE><<<grid, 256>>>(ix->dev, job);
+            if (ix->codec == CODEC_OPTPFOR) decode_blocks_kernel<CODEC_OPTPFOR><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
+            else if (ix->codec == CODEC_INTERPOLATIVE) decode_blocks_kernel<CODEC_INTERPOLATIVE><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
             else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
         }
     }
@@ -603,19 +633,17 @@ struct GeqJob {
 
 template <int CODEC>
 __global__ void __launch_bounds__(128) next_geq_kernel(DevIndex idx, GeqJob job) {
-    __shared__ __align__(16) uint8_t smem_raw[4 * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16)];
-    __shared__ uint32_t s16tab[S16_TAB_WORDS];
-    s16_table_init(s16tab);
+    s16_table_init(smem_words(0));
     __syncthreads();
     typedef BlockEnum<CODEC> E;
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* base = smem_raw + warp * (sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16);
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * SINGLE_LIST_WARP_BYTES;
     ListState* st = reinterpret_cast<ListState*>(base);
     uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(ListState));
     uint32_t* scratch = stage + STAGE_WORDS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
     WarpCtx c;
-    ctx_init(c, stage, scratch, bar, s16tab);
+    ctx_init(c, stage, scratch, bar);
     while (true) {
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(job.work_counter, 1u);
@@ -657,8 +685,8 @@ extern "C" int ds2i_gpu_next_geq_batch(ds2i_gpu_index* ix, const uint32_t* terms
         } else {
             GeqJob job{d_terms.p, d_bounds.p, d_offs.p, d_docids.p, d_freqs.p, d_counter.p, uint32_t(nlists)};
             int grid = int(std::min<uint64_t>((nlists + 3) / 4, uint64_t(ix->sm_count) * 8));
-            if (ix->codec == CODEC_OPTPFOR) next_geq_kernel<CODEC_OPTPFOR><<<grid, 128>>>(ix->dev, job);
-            else if (ix->codec == CODEC_INTERPOLATIVE) next_geq_kernel<CODEC_INTERPOLATIVE><<<grid, 128>>>(ix->dev, job);
+            if (ix->codec == CODEC_OPTPFOR) next_geq_kernel<CODEC_OPTPFOR><<<grid, 128, S16_TAB_BYTES + 4 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
+            else if (ix->codec == CODEC_INTERPOLATIVE) next_geq_kernel<CODEC_INTERPOLATIVE><<<grid, 128, S16_TAB_BYTES + 4 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
             else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
         }
     }

@@ -83,22 +83,20 @@ __host__ __device__ constexpr size_t warp_smem_bytes(int slots) {
 
 template <int CODEC, int OP>
 __global__ void __launch_bounds__(128) query_kernel(DevIndex idx, DevWand wand, DevBatch batch, uint32_t k, int slots) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t s16tab[S16_TAB_WORDS];
-    s16_table_init(s16tab);
+    s16_table_init(smem_words(0));
     __syncthreads();
 
     typedef BlockEnum<CODEC> E;
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    uint8_t* base = smem_raw + warp * warp_smem_bytes(slots);
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes(slots);
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
     ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
     uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState));
     uint32_t* scratch = stage + STAGE_WORDS;
 
     WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar, s16tab);
+    ctx_init(c, stage, scratch, &ws->bar);
     const uint32_t N = idx.num_docs;
     constexpr bool RANKED = (OP == OP_RANKED_AND || OP == OP_WAND || OP == OP_MAXSCORE || OP == OP_RANKED_OR);
 
