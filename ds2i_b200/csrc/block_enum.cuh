@@ -33,6 +33,11 @@ struct ListState {
     uint32_t block_end;     // offset (from data_off) of the end of the current block
     uint32_t freqs_ready;
     uint32_t pad;
+    // used by the block-parallel kernels
+    uint32_t prev_max;      // block_max of the block before the current one (0xffffffff for block 0)
+    uint32_t last_max;      // last docid of the list
+    uint32_t win_block;     // block the list sat on when the current window started
+    uint32_t exhausted;
     uint32_t docs[BLOCK];   // absolute docids of the current block (0xffffffff beyond cur_size)
     uint32_t freqs[BLOCK];  // freqs - 1 of the current block, valid when freqs_ready
 };
@@ -169,7 +174,7 @@ struct BlockEnum {
             gaps_to_docids128(st->docs, cur_base);
         }
         if (lane == 0) {
-            st->cur_block = b; st->pos = 0; st->cur_size = size; st->cur_max = cur_max;
+            st->cur_block = b; st->pos = 0; st->cur_size = size; st->cur_max = cur_max; st->prev_max = prev_max;
             st->cur_docid = st->docs[0];
             st->freqs_off = e0 + consumed; st->block_end = e1; st->freqs_ready = 0;
         }

@@ -23,6 +23,7 @@
 #include "format.hpp"
 #include "query_kernels.cuh"
 #include "and_kernels.cuh"
+#include "union_kernels.cuh"
 #include "pef_kernels.cuh"
 
 using namespace ds2i_gpu;
@@ -116,6 +117,11 @@ struct ds2i_gpu_batch {
     dev_buf<uint32_t> and_order, and_item_begin, and_item_counts, and_item_sizes;
     dev_buf<float> and_item_scores;
     uint32_t n_and_items = 0, n_and_items_large = 0;
+    // block-parallel union path (wand / maxscore): work items = (query, docid range)
+    dev_buf<UnionItem> un_items;
+    dev_buf<uint32_t> un_order, un_item_begin, un_item_sizes, un_threshold;
+    dev_buf<float> un_item_scores;
+    uint32_t n_un_items = 0;
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~ds2i_gpu_batch() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
@@ -337,6 +343,32 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
     CUDA_TRY(b->and_item_scores.alloc(items.size() * MAX_K));
 
+    // work items of the union path: heavy queries are cut into docid ranges
+    {
+        std::vector<UnionItem> uitems;
+        std::vector<uint32_t> ubegin(nq + 1, 0), uorder;
+        // postings per work item; DS2I_GPU_UNION_ITEM_POSTINGS overrides it (tests use a tiny value to
+        // exercise the range-splitting path on small collections)
+        uint64_t per_item = 32768;
+        if (const char* ev = getenv("DS2I_GPU_UNION_ITEM_POSTINGS")) per_item = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
+        for (size_t q = 0; q < nq; ++q) {
+            if (q_begin[q + 1] > q_begin[q]) {
+                uint64_t r = std::min<uint64_t>(64, std::max<uint64_t>(1, (cost[q] + per_item - 1) / per_item));
+                for (uint64_t i = 0; i < r; ++i) {
+                    uint64_t lo = ix->num_docs * i / r, hi = ix->num_docs * (i + 1) / r;
+                    if (hi > lo) uitems.push_back(UnionItem{uint32_t(q), uint32_t(lo), uint32_t(hi)});
+                }
+            }
+            ubegin[q + 1] = uint32_t(uitems.size());
+        }
+        for (uint32_t qi : sched)
+            for (uint32_t it = ubegin[qi]; it < ubegin[qi + 1]; ++it) uorder.push_back(it);
+        b->n_un_items = uint32_t(uitems.size());
+        CUDA_TRY(b->un_items.upload(uitems)); CUDA_TRY(b->un_order.upload(uorder)); CUDA_TRY(b->un_item_begin.upload(ubegin));
+        CUDA_TRY(b->un_item_sizes.alloc(uitems.size())); CUDA_TRY(b->un_item_scores.alloc(uitems.size() * MAX_K));
+        CUDA_TRY(b->un_threshold.alloc(nq));
+    }
+
     b->max_terms = max_terms;
     CUDA_TRY(b->q_begin.upload(q_begin)); CUDA_TRY(b->term.upload(term)); CUDA_TRY(b->sched.upload(sched));
     CUDA_TRY(b->q_weight.upload(q_weight)); CUDA_TRY(b->max_weight.upload(max_weight));
@@ -398,6 +430,27 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
 }
 
 template <int CODEC>
+static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
+    ds2i_gpu_index* ix = b->index;
+    const int warps = 4;
+    auto kern = union_block_kernel<CODEC>;
+    size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(b->max_terms + 1);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return fail(DS2I_E_CUDA, "union kernel does not fit on an SM");
+    int grid = per_sm * ix->sm_count;
+    int needed = int((b->n_un_items + warps - 1) / warps);
+    if (grid > needed) grid = std::max(needed, 1);
+    CUDA_TRY(cudaMemsetAsync(b->un_threshold.p, 0, std::max<size_t>(b->nq, 1) * sizeof(uint32_t)));
+    UnionJob job{b->un_items.p, b->un_order.p, b->n_un_items, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
+    if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, b->wand->dev, db, job, k, b->max_terms); b->launches += 1; }
+    merge_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_sizes.p, b->un_item_scores.p,
+                                                 k, true, b->out_counts.p, b->out_scores.p);
+    return DS2I_OK;
+}
+
+template <int CODEC>
 static int launch_query_op(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32_t k) {
     switch (op) {
         case OP_AND: return launch_query<CODEC, OP_AND>(b, db, k);
@@ -439,6 +492,11 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
             if (!ranked) k = 1;
             if (ix->codec == CODEC_OPTPFOR) rc = op == OP_AND ? launch_and_block<CODEC_OPTPFOR, false>(b, db, k) : launch_and_block<CODEC_OPTPFOR, true>(b, db, k);
             else if (ix->codec == CODEC_INTERPOLATIVE) rc = op == OP_AND ? launch_and_block<CODEC_INTERPOLATIVE, false>(b, db, k) : launch_and_block<CODEC_INTERPOLATIVE, true>(b, db, k);
+            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+        }
+        else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE)) {
+            if (ix->codec == CODEC_OPTPFOR) rc = launch_union_block<CODEC_OPTPFOR>(b, db, k);
+            else if (ix->codec == CODEC_INTERPOLATIVE) rc = launch_union_block<CODEC_INTERPOLATIVE>(b, db, k);
             else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
         }
         else if (ix->codec == CODEC_OPTPFOR) rc = launch_query_op<CODEC_OPTPFOR>(b, db, op, k);

@@ -1,0 +1,363 @@
+// Block-parallel dynamic-pruning top-k over the UNION of the query's lists: the device path behind
+// wand_query and maxscore_query (queries.hpp:200-319, 478-591).
+//
+// Both reference operators are rank-safe: they return the k best BM25 scores of the documents that
+// contain at least one query term, and differ only in how they skip documents that provably cannot
+// enter the heap.  Their control flow is one document at a time with the heap threshold fed back
+// after every insert — sequential.  This kernel keeps MaxScore's pruning logic (lists sorted by
+// max_weight, prefix sums ub[], "essential" lists whose postings are the only candidates,
+// non-essential lists probed from the highest bound down while score + ub[i] can still enter,
+// queries.hpp:519-578) but evaluates it 128 candidates at a time:
+//   * a window = the docids up to the smallest current block_max of the essential lists; the
+//     postings of each essential list inside the window are candidates, 4 per lane;
+//   * essential contributions: 128-wide binary search of the other essential lists' decoded blocks
+//     (a document is scored by the first essential list that contains it);
+//   * non-essential lists: the block-at-a-time probing of and_kernels.cuh, restricted to the
+//     candidates for which would_enter(score + ub[i]) still holds;
+//   * only scores above the running threshold reach the serial top-k insert.
+// Pruning with a stale (lower) threshold is always safe, so the top-k multiset equals the
+// reference's; per-document sums follow MaxScore's order (essential lists by increasing max_weight,
+// then non-essential ones downwards) but which lists are essential depends on the threshold
+// history, so scores can differ from the reference in the last bit — within the 1e-5 relative
+// tolerance of the north star (the literal, bit-exact kernels stay available: DS2I_RUN_FAITHFUL).
+//
+// Work item = (query, docid range).  Items of one query share a monotone global threshold
+// (atomicMax on the float bits), so splitting a heavy query over many warps keeps its pruning power.
+#pragma once
+#include "and_kernels.cuh"
+
+namespace ds2i_gpu {
+
+struct UnionItem { uint32_t query, lo, hi; };      // docid range [lo, hi)
+
+struct UnionJob {
+    const UnionItem* items;      // in query order
+    const uint32_t* order;       // processing order
+    uint32_t nitems;
+    uint32_t* work_counter;
+    uint32_t* query_threshold;   // nq: float bits of the best published k-th score of the query
+    uint32_t* item_sizes;
+    float* item_scores;          // nitems * k
+};
+
+// top-k with a floor shared across the items of a query
+struct TopKShared {
+    TopK t;
+    float floor_;     // published k-th best score of the whole query so far (0 = none)
+    __device__ __forceinline__ void init(uint32_t k) { t.init(k); floor_ = 0.f; }
+    __device__ __forceinline__ float bar() const { return t.size < t.k ? floor_ : fmaxf(t.thr, floor_); }
+    __device__ __forceinline__ bool would_enter(float s) const { return s > bar(); }
+    __device__ __forceinline__ void insert(float s) { if (would_enter(s)) t.insert(s); }
+};
+
+template <int CODEC>
+struct UnionOps {
+    typedef BlockEnum<CODEC> E;
+
+    // freqs of the list's current block as plain values (freq - 1) in dst[0..size)
+    static __device__ __forceinline__ void decode_freqs_plain(WarpCtx& c, DevIndex const& idx, ListState* s, uint32_t* dst) {
+        const unsigned lane = lane_id();
+        uint32_t off = stage_range(c, idx.lists, s->data_off + s->freqs_off, s->data_off + s->block_end);
+        bool prefix;
+        uint32_t size = s->cur_size;
+        uint32_t consumed = decode_values<CODEC>(c, off, size, 0xffffffffu, dst, prefix);
+        c.c_freqs_blocks += 1; c.c_freqs_bytes += consumed;
+        if (prefix) {
+            uint32_t d[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                uint32_t i = 32 * j + lane;
+                d[j] = (i < size) ? dst[i] - (i ? dst[i - 1] : 0u) : 0u;
+            }
+            __syncwarp();
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) dst[32 * j + lane] = d[j];
+            __syncwarp();
+        }
+    }
+
+    static __device__ __forceinline__ uint32_t count_less(const ListState* s, uint32_t bound) {
+        uint4 v = reinterpret_cast<const uint4*>(s->docs)[lane_id()];
+        uint32_t cnt = (v.x < bound) + (v.y < bound) + (v.z < bound) + (v.w < bound);
+        return __reduce_add_sync(FULL, cnt);
+    }
+
+    // essential list: docs + freqs of block b, cursor at its first element
+    static __device__ __forceinline__ void load_essential_block(WarpCtx& c, DevIndex const& idx, ListState* s, uint32_t b) {
+        E::decode_docs_block(c, idx, s, b);
+        if (b + 1 < s->nblocks) prefetch_l2(idx.lists + s->data_off + s->block_end + lane_id() * 32u);
+        decode_freqs_plain(c, idx, s, s->freqs);
+        if (lane_id() == 0) s->freqs_ready = 1;
+        __syncwarp();
+    }
+};
+
+template <int CODEC>
+__global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, UnionJob job, uint32_t k, int slots) {
+    s16_table_init(smem_words(0));
+    __syncthreads();
+
+    typedef BlockEnum<CODEC> E;
+    typedef UnionOps<CODEC> U;
+    const unsigned lane = lane_id();
+    const unsigned warp = threadIdx.x >> 5;
+    // one extra ListState-sized slot at the end serves as the freqs scratch of probed lists
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes(slots + 1);
+    WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
+    ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
+    uint32_t* ftmp = st[slots].docs;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots + 1) * sizeof(ListState));
+    uint32_t* scratch = stage + STAGE_WORDS;
+
+    WarpCtx c;
+    ctx_init(c, stage, scratch, &ws->bar);
+
+    while (true) {
+        uint32_t ii = 0;
+        if (lane == 0) ii = atomicAdd(job.work_counter, 1u);
+        ii = __shfl_sync(FULL, ii, 0);
+        if (ii >= job.nitems) break;
+        ii = job.order[ii];
+        const UnionItem item = job.items[ii];
+        const uint32_t q = item.query;
+        const uint32_t t0 = batch.q_begin[q];
+        const uint32_t nt = batch.q_begin[q + 1] - t0;
+        const uint32_t lo = item.lo, hi = item.hi;
+        TopKShared topk;
+        topk.init(k);
+
+        // slots in increasing max_weight order (queries.hpp:521-524), upper bounds by sequential prefix sum (:526-530)
+        __syncwarp();
+        if (lane < nt) {
+            uint32_t src = batch.ord_maxw[t0 + lane];
+            ws->qw[lane] = batch.q_weight[t0 + src];
+            ws->mw[lane] = batch.max_weight[t0 + src];
+            ListDir d = idx.dir[batch.term[t0 + src]];
+            uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+            ListState* s = &st[lane];
+            s->maxs_off = d.maxs_off;
+            s->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
+            s->n = d.n; s->nblocks = nblocks; s->data_bytes = d.data_bytes;
+            s->cur_block = 0xffffffffu; s->cur_max = 0; s->prev_max = 0xffffffffu; s->cur_size = 0; s->pos = 0;
+            s->freqs_ready = 0; s->win_block = 0xffffffffu;
+            s->last_max = ldg_u32_unaligned(idx.lists + d.maxs_off + 4ull * (nblocks - 1));
+            s->exhausted = s->last_max < lo ? 1u : 0u;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float acc = ws->mw[0];
+            ws->ub[0] = acc;
+            for (uint32_t i = 1; i < nt; ++i) { acc = acc + ws->mw[i]; ws->ub[i] = acc; }
+        }
+        __syncwarp();
+
+        uint32_t ne = 0;                 // lists [0, ne) are non-essential
+        uint32_t positioned = 0;         // bit i: list i has been positioned as an essential list
+        while (true) {
+            // refresh the shared floor, grow the non-essential prefix (queries.hpp:568-574)
+            {
+                uint32_t g = 0;
+                if (lane == 0) g = *reinterpret_cast<volatile uint32_t*>(job.query_threshold + q);
+                g = __shfl_sync(FULL, g, 0);
+                topk.floor_ = fmaxf(topk.floor_, __uint_as_float(g));
+            }
+            while (ne < nt && !topk.would_enter(ws->ub[ne])) ne += 1;
+            if (ne == nt) break;
+
+            // essential lists that have not been opened yet: position them at the start of the range
+            for (uint32_t e = ne; e < nt; ++e) {
+                if (positioned & (1u << e)) continue;
+                positioned |= 1u << e;
+                ListState* s = &st[e];
+                if (s->exhausted) continue;
+                uint32_t cb = s->cur_block;
+                if (cb == 0xffffffffu || s->cur_max < lo) {
+                    // never touched (or left behind as a probed list): find the block holding the first docid >= lo
+                    bool fresh = cb == 0xffffffffu;
+                    BlockMeta bm = find_block(c, s, idx.lists + s->maxs_off, fresh ? 0u : cb + 1, fresh ? 0xffffffffu : s->cur_max, lo);
+                    U::load_essential_block(c, idx, s, bm.block);
+                    uint32_t p = U::count_less(s, lo);
+                    if (lane == 0) s->pos = p;
+                    __syncwarp();
+                } else if (!s->freqs_ready) {
+                    // was a probed (non-essential-style) list positioned inside the range: keep its cursor
+                    U::decode_freqs_plain(c, idx, s, s->freqs);
+                    if (lane == 0) s->freqs_ready = 1;
+                    __syncwarp();
+                }
+            }
+
+            // window: everything up to the smallest current block_max of the live essential lists
+            uint32_t w_hi = 0xffffffffu;
+            bool any = false;
+            for (uint32_t e = ne; e < nt; ++e) {
+                const ListState* s = &st[e];
+                if (s->exhausted) continue;
+                any = true;
+                w_hi = min(w_hi, s->cur_max);
+            }
+            if (!any) break;
+            if (w_hi >= hi) w_hi = hi - 1;
+            for (uint32_t i = 0; i < ne; ++i) if (lane == 0) st[i].win_block = st[i].cur_block;
+            __syncwarp();
+
+            for (uint32_t e = ne; e < nt; ++e) {
+                ListState* se = &st[e];
+                if (se->exhausted) continue;
+                const uint32_t pos_e = se->pos;
+                const uint32_t end_e = U::count_less(se, w_hi + 1u);       // elements <= w_hi
+                if (end_e <= pos_e) continue;
+                // candidates of this group: positions [pos_e, end_e) of list e's block
+                uint32_t cand[4], alive = 0;
+                float score[4], nl[4];
+                {
+                    uint4 cv = reinterpret_cast<const uint4*>(se->docs)[lane];
+                    cand[0] = cv.x; cand[1] = cv.y; cand[2] = cv.z; cand[3] = cv.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t slot = 4 * lane + j;
+                    if (slot >= pos_e && slot < end_e) alive |= 1u << j;
+                    score[j] = 0.f; nl[j] = 0.f;
+                }
+                // essential part, lists in increasing max_weight order; a document belongs to the first
+                // essential list that contains it
+                for (uint32_t e2 = ne; e2 < nt; ++e2) {
+                    if (e2 == e) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (alive & (1u << j)) {
+                                if (e2 == ne || nl[j] == 0.f) nl[j] = __ldg(wand.norm_lens + cand[j]);
+                                score[j] += ws->qw[e] * doc_term_weight(se->freqs[4 * lane + j] + 1u, nl[j]);
+                            }
+                        continue;
+                    }
+                    const ListState* s2 = &st[e2];
+                    if (s2->exhausted) continue;
+                    const uint32_t* d2 = s2->docs;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (alive & (1u << j)) {
+                            uint32_t p = lower_bound128(d2, cand[j]);
+                            if (d2[p] == cand[j]) {
+                                if (e2 < e) alive &= ~(1u << j);       // already scored from list e2's group
+                                else {
+                                    if (nl[j] == 0.f) nl[j] = __ldg(wand.norm_lens + cand[j]);
+                                    score[j] += ws->qw[e2] * doc_term_weight(s2->freqs[p] + 1u, nl[j]);
+                                }
+                            }
+                        }
+                }
+                unsigned n_owned = __reduce_add_sync(FULL, __popc(alive));
+                c.c_scored += n_owned;
+
+                // non-essential lists from the highest bound down (queries.hpp:557-566)
+                uint32_t probing = alive;
+                for (uint32_t i = ne; i-- > 0;) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((probing & (1u << j)) && !topk.would_enter(score[j] + ws->ub[i])) probing &= ~(1u << j);
+                    if (!__any_sync(FULL, probing)) break;
+                    ListState* s = &st[i];
+                    if (s->exhausted) continue;
+                    const uint8_t* maxs = idx.lists + s->maxs_off;
+                    uint32_t pending = probing;
+                    bool first_lookup = true;
+                    while (true) {
+                        uint32_t mine = 0xffffffffu;
+#pragma unroll
+                        for (int j = 3; j >= 0; --j) if (pending & (1u << j)) mine = cand[j];
+                        uint32_t cmin = __reduce_min_sync(FULL, mine);
+                        if (cmin == 0xffffffffu) break;
+                        if (cmin > s->last_max) break;                 // nothing of list i at or beyond cmin
+                        uint32_t cur_block = s->cur_block;
+                        if (first_lookup && cur_block != 0xffffffffu && s->prev_max != 0xffffffffu && cmin <= s->prev_max) {
+                            // an earlier group of this window moved the cursor past cmin: step back to where the window began
+                            uint32_t wb = s->win_block;
+                            if (wb == 0xffffffffu) {
+                                if (lane == 0) { s->cur_block = 0xffffffffu; s->cur_max = 0; s->prev_max = 0xffffffffu; }
+                                __syncwarp();
+                            } else {
+                                E::decode_docs_block(c, idx, s, wb);
+                            }
+                            cur_block = s->cur_block;
+                        }
+                        first_lookup = false;
+                        if (cur_block == 0xffffffffu || cmin > s->cur_max) {
+                            bool fresh = cur_block == 0xffffffffu;
+                            BlockMeta bm = find_block(c, s, maxs, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max, cmin);
+                            if (bm.have) E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+                            else E::decode_docs_block(c, idx, s, bm.block);
+                        }
+                        const uint32_t cur_max = s->cur_max;
+                        const uint32_t* d = s->docs;
+                        uint32_t hitmask = 0, pos[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            pos[j] = 0;
+                            if ((pending & (1u << j)) && cand[j] <= cur_max) {
+                                pos[j] = lower_bound128(d, cand[j]);
+                                if (d[pos[j]] == cand[j]) hitmask |= 1u << j;
+                                pending &= ~(1u << j);
+                            }
+                        }
+                        if (__any_sync(FULL, hitmask)) {
+                            U::decode_freqs_plain(c, idx, s, ftmp);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (hitmask & (1u << j)) score[j] += ws->qw[i] * doc_term_weight(ftmp[pos[j]] + 1u, nl[j]);
+                            __syncwarp();
+                        }
+                    }
+                }
+
+                // heap: only scores that can still enter
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned want = __ballot_sync(FULL, (alive & (1u << j)) && topk.would_enter(score[j]));
+                    while (want) {
+                        int src = __ffs(want) - 1;
+                        want &= want - 1;
+                        float sc = __shfl_sync(FULL, score[j], src);
+                        topk.insert(sc);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) se->pos = end_e;
+                __syncwarp();
+            }
+
+            // publish the threshold, then move consumed essential lists to their next block
+            if (topk.t.size == topk.t.k && topk.t.thr > topk.floor_) {
+                if (lane == 0) atomicMax(job.query_threshold + q, __float_as_uint(topk.t.thr));
+            }
+            bool range_done = (w_hi + 1u >= hi);
+            for (uint32_t e = ne; e < nt; ++e) {
+                ListState* s = &st[e];
+                if (s->exhausted) continue;
+                if (range_done) { if (lane == 0) s->exhausted = 1; continue; }
+                if (s->pos >= s->cur_size) {
+                    uint32_t nb = s->cur_block + 1;
+                    if (nb >= s->nblocks || s->cur_max + 1u >= hi) { __syncwarp(); if (lane == 0) s->exhausted = 1; __syncwarp(); }
+                    else U::load_essential_block(c, idx, s, nb);
+                }
+            }
+            __syncwarp();
+            if (range_done) break;
+        }
+
+        if (lane == 0) job.item_sizes[ii] = topk.t.size;
+        if (lane < k) job.item_scores[size_t(ii) * k + lane] = lane < topk.t.size ? topk.t.v : 0.f;
+    }
+
+    if (batch.stats && lane == 0) {
+        atomicAdd(&batch.stats[0], (unsigned long long)c.c_docs_blocks);
+        atomicAdd(&batch.stats[1], (unsigned long long)c.c_freqs_blocks);
+        atomicAdd(&batch.stats[2], (unsigned long long)c.c_docs_bytes);
+        atomicAdd(&batch.stats[3], (unsigned long long)c.c_freqs_bytes);
+        atomicAdd(&batch.stats[4], (unsigned long long)c.c_maxs);
+        atomicAdd(&batch.stats[5], (unsigned long long)c.c_scored);
+    }
+}
+
+}  // namespace ds2i_gpu

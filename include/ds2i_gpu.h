@@ -91,8 +91,11 @@ int ds2i_gpu_batch_prepare(ds2i_gpu_index*, ds2i_gpu_wand*, const uint32_t* term
                            const uint64_t* query_offsets, size_t nq, ds2i_gpu_batch** out);
 int ds2i_gpu_batch_run(ds2i_gpu_batch*, int op, uint32_t k, float* out_elapsed_ms);   /* device only, synchronises */
 /* flags: DS2I_RUN_FAITHFUL evaluates with the reference's own control flow, one warp per query, one
- * candidate at a time (same blocks decoded as the reference; the slow, literal kernels).  Without it
- * and / ranked_and use the block-at-a-time kernels (same results, bit for bit). */
+ * candidate at a time (same blocks decoded as the reference; the slow, literal kernels; scores
+ * bit-identical to a -ffp-contract=off build of the reference).  Without it and / ranked_and use the
+ * block-at-a-time kernels (same results, bit for bit) and wand / maxscore use the block-parallel
+ * dynamic-pruning kernel (same top-k; a score may differ from the reference in the last bit because
+ * the BM25 summation order follows the pruning state — within 1e-5 relative). */
 #define DS2I_RUN_FAITHFUL 1u
 int ds2i_gpu_batch_run_ex(ds2i_gpu_batch*, int op, uint32_t k, uint32_t flags, float* out_elapsed_ms);
 int ds2i_gpu_batch_fetch(ds2i_gpu_batch*, uint64_t* out_counts, float* out_scores);   /* D2H of the last run */
