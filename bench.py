@@ -243,7 +243,9 @@ def main():
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_s = float(te_t.item())
-    assert np.array_equal(c2, counts) and np.array_equal(s2.view(np.uint32), scores.view(np.uint32))
+    # same results through both entry points (the union kernel's last score bit depends on the pruning history)
+    assert np.array_equal(c2, counts)
+    assert np.all(np.abs(s2.astype(np.float64) - scores) <= 1e-5 * np.maximum(np.abs(scores), 1e-30))
     nterms = sum(len(q) for q in queries)
     h2d = nterms * 4 + (len(queries) + 1) * 8
     d2h = len(queries) * 8 + len(queries) * args.k * 4
@@ -295,7 +297,9 @@ def main():
                 ec, es = load_dump(tmp, (args.op,))[args.op]
                 ok_counts = bool(np.array_equal(ec, counts[:ncheck]))
                 ok_scores = bool(np.array_equal(es.view(np.uint32), scores[:ncheck].view(np.uint32)))
-                line["parity"] = {"queries_checked": ncheck, "counts_bit_exact": ok_counts, "scores_bit_exact": ok_scores}
+                rel = float(np.max(np.abs(es.astype(np.float64) - scores[:ncheck]) / np.maximum(np.abs(es), 1e-30)))
+                line["parity"] = {"queries_checked": ncheck, "counts_bit_exact": ok_counts, "scores_bit_exact": ok_scores,
+                                  "scores_max_rel_err": rel, "tolerance": 1e-5, "against": "ds2i reference, -ffp-contract=off build"}
         except Exception as e:   # the baseline is a report, never a reason to lose the measurement
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
     print(json.dumps(line), flush=True)

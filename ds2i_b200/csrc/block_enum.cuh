@@ -22,6 +22,7 @@ struct DevIndex {
     const ListDir* dir;
     uint64_t num_lists;
     uint32_t num_docs;
+    int codec;              // CODEC_*
 };
 
 struct ListState {
@@ -48,14 +49,15 @@ struct WarpCtx {
     uint32_t* scratch;      // SCRATCH_WORDS
     uint64_t* bar;
     uint32_t phase;
+    int codec;              // CODEC_* of the index (used when kernels are instantiated with CODEC_ANY)
     uint64_t win_start;     // absolute byte range currently staged
     uint32_t win_bytes;
     // counters (SURVEY.md §8d algorithmic bytes)
     uint32_t c_docs_blocks, c_freqs_blocks, c_docs_bytes, c_freqs_bytes, c_maxs, c_scored;
 };
 
-__device__ __forceinline__ void ctx_init(WarpCtx& c, uint32_t* stage, uint32_t* scratch, uint64_t* bar) {
-    c.stage = stage; c.scratch = scratch; c.bar = bar;
+__device__ __forceinline__ void ctx_init(WarpCtx& c, uint32_t* stage, uint32_t* scratch, uint64_t* bar, int codec) {
+    c.stage = stage; c.scratch = scratch; c.bar = bar; c.codec = codec;
     c.phase = 0; c.win_start = 0; c.win_bytes = 0;
     c.c_docs_blocks = c.c_freqs_blocks = c.c_docs_bytes = c.c_freqs_bytes = c.c_maxs = c.c_scored = 0;
     if (lane_id() == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -103,9 +105,12 @@ __device__ __forceinline__ void gaps_to_docids128(uint32_t* buf, uint32_t base) 
 template <int CODEC>
 __device__ __forceinline__ uint32_t decode_values(WarpCtx& c, uint32_t off, uint32_t size, uint32_t sum_of_values,
                                                   uint32_t* buf, bool& prefix_out) {
-    if (CODEC != CODEC_INTERPOLATIVE && size == BLOCK) {
+    const int codec = (CODEC == CODEC_ANY) ? c.codec : CODEC;
+    if (codec != CODEC_INTERPOLATIVE && size == BLOCK) {
         prefix_out = false;
-        if (CODEC == CODEC_OPTPFOR) return decode_optpfor128(smem_offset(c.stage), off, smem_offset(buf), smem_offset(c.scratch));
+        if (codec == CODEC_OPTPFOR) return decode_optpfor128(smem_offset(c.stage), off, smem_offset(buf), smem_offset(c.scratch));
+        if (codec == CODEC_VARINT) return decode_varint128(smem_offset(c.stage), off, smem_offset(buf));
+        return decode_qmx128(smem_offset(c.stage), off, smem_offset(buf));
     }
     // n < block_size => every codec falls back to interpolative (block_codecs.hpp:196-199,215-217)
     prefix_out = true;

@@ -9,7 +9,7 @@
 
 namespace ds2i_gpu {
 
-enum : int { CODEC_OPTPFOR = 0, CODEC_VARINT = 1, CODEC_INTERPOLATIVE = 2, CODEC_QMX = 3 };
+enum : int { CODEC_OPTPFOR = 0, CODEC_VARINT = 1, CODEC_INTERPOLATIVE = 2, CODEC_QMX = 3, CODEC_ANY = 99 /* decided at run time from the index */ };
 
 constexpr uint32_t BLOCK = 128;            // BlockCodec::block_size for every codec
 constexpr uint32_t SCRATCH_WORDS = 320;    // Simple16 output (<= 2*128 + 27) / interpolative stack
@@ -153,6 +153,152 @@ __device__ __noinline__ uint32_t decode_optpfor128(uint32_t win_off, uint32_t of
     }
     __syncwarp();
     return 4u * (1u + excw + 4u * b);
+}
+
+
+// ---- varint-G8IU block of exactly 128 values (FastPFor/headers/VarIntG8IU.h:152-195; ds2i decode
+// block_codecs.hpp:239-258,287-314).  9-byte groups: descriptor + 8 data bytes; bit i of the
+// descriptor is 0 iff data byte i ends an integer.  The group count is not stored: lane g reads the
+// descriptors of groups g and g+32, a warp scan of the per-group integer counts finds the group that
+// completes the 128th value (bytes after it belong to the next block and are never interpreted), and
+// every lane then expands its own groups.
+__device__ __noinline__ uint32_t decode_varint128(uint32_t win_off, uint32_t off, uint32_t out_off) {
+    const uint32_t* win = smem_words(win_off);
+    uint32_t* out = smem_words(out_off);
+    const unsigned lane = lane_id();
+    uint32_t carry = 0, groups = 0;
+    for (uint32_t round = 0; round < 2 && carry < BLOCK; ++round) {
+        const uint32_t g = round * 32 + lane;
+        const uint32_t gb = off + 9u * g;
+        const uint32_t desc = lds_u8(win, gb);
+        const uint32_t lo = lds_u32(win, gb + 1), hi = lds_u32(win, gb + 5);
+        uint32_t cnt = 8u - __popc(desc);
+        uint32_t incl = warp_inclusive_scan(cnt);
+        uint32_t base = carry + incl - cnt;
+        bool live = base < BLOCK;                      // groups that start before the 128th value
+        if (live) {
+            uint32_t idx = base, cur = 0, shift = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+                uint32_t byte = ((i < 4 ? lo : hi) >> (8u * (i & 3u))) & 0xffu;
+                cur |= byte << shift;
+                shift += 8;
+                if (!((desc >> i) & 1u)) {
+                    if (idx < BLOCK) out[idx] = cur;
+                    ++idx; cur = 0; shift = 0;
+                }
+            }
+        }
+        groups += __popc(__ballot_sync(FULL, live));
+        carry += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    return 9u * groups;
+}
+
+// ---- QMX block of exactly 128 values (qmx_codec.hpp:636-6115; ds2i wrapper block_codecs.hpp:317-350).
+// TightVByte(len), then `len` bytes: payload stripes first, the key bytes in REVERSE order at the
+// end.  key = type << 4 | (16 - run); the decoder consumes keys backwards while the payload cursor
+// has not passed them (:655-656).  Lane t owns the t-th key from the end: two warp scans give every
+// key's first payload byte and first output index; then each lane extracts "its" outputs by locating
+// the key with a shuffle search.  128-bit stripes are four interleaved u32 lanes (value v in lane
+// v & 3, row v >> 2); 8/16/32-bit types are sequential; the four 256-bit types (7, 9, 12, 21 bits)
+// straddle a (lo, hi) stripe pair as tabulated below (:4833-4856, :5310-5338, :5700-5724, :5980-5998).
+__device__ __noinline__ uint32_t decode_qmx128(uint32_t win_off, uint32_t off, uint32_t out_off) {
+    const uint32_t* win = smem_words(win_off);
+    uint32_t* out = smem_words(out_off);
+    const unsigned lane = lane_id();
+    uint32_t p0 = off;
+    const uint32_t len = vbyte_decode(win, p0);
+    // per type: values per stripe unit, payload bytes per unit, bit width
+    auto type_count = [](uint32_t t) -> uint32_t {
+        // {256,128,64,40,32,24,20,36,16,28,12,20,8,12,4,0}
+        const uint32_t tab[16] = {256, 128, 64, 40, 32, 24, 20, 36, 16, 28, 12, 20, 8, 12, 4, 0};
+        uint32_t r = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) r = (t == i) ? tab[i] : r;
+        return r;
+    };
+    auto type_bytes = [](uint32_t t) -> uint32_t {
+        if (t == 0) return 0u;
+        if (t == 15) return 1u;
+        return (t == 7 || t == 9 || t == 11 || t == 13) ? 32u : 16u;
+    };
+    auto type_width = [](uint32_t t) -> uint32_t {
+        const uint32_t tab[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 21, 32, 0};
+        uint32_t r = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) r = (t == i) ? tab[i] : r;
+        return r;
+    };
+
+    uint32_t pcarry = 0, icarry = 0;
+    for (uint32_t kbase = 0; kbase < len && icarry < BLOCK; kbase += 32) {
+        const uint32_t T = kbase + lane;
+        const bool inrange = T < len;
+        const uint32_t key = inrange ? lds_u8(win, p0 + len - 1u - T) : 0xffu;
+        const uint32_t type = key >> 4, run = 16u - (key & 15u);
+        const uint32_t cnt = type_count(type);
+        const uint32_t ub = type_bytes(type);
+        uint32_t nbytes = inrange ? run * ub : 0u, nints = inrange ? run * cnt : 0u;
+        uint32_t pincl = warp_inclusive_scan(nbytes);
+        uint32_t pexcl = pcarry + pincl - nbytes;
+        // "while (in <= keys)": key T is consumed iff the payload cursor has not passed it
+        bool valid = inrange && pexcl <= len - 1u - T;
+        unsigned vmask = __ballot_sync(FULL, valid);
+        unsigned first_bad = __ffs(~vmask);                       // keys are consumed in order: stop at the first refusal
+        uint32_t nvalid = first_bad ? first_bad - 1u : 32u;
+        if (lane >= nvalid) nints = 0;
+        uint32_t iincl = warp_inclusive_scan(nints);
+        uint32_t iexcl = icarry + iincl - nints;                  // first output index of this key
+        const uint32_t round_end = icarry + __shfl_sync(FULL, iincl, 31);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t i = 32u * j + lane;
+            // key holding output i (largest t with iexcl_t <= i among keys with ints)
+            uint32_t t = 0;
+#pragma unroll
+            for (uint32_t s = 16; s >= 1; s >>= 1) {
+                uint32_t st = __shfl_sync(FULL, iexcl, (t + s) & 31u);
+                if (st <= i) t += s;
+            }
+            // (a key without values shares its start index with its successor, which the search prefers)
+            uint32_t kb = __shfl_sync(FULL, iexcl, t), kn = __shfl_sync(FULL, nints, t);
+            uint32_t ktype = __shfl_sync(FULL, type, t), kp = __shfl_sync(FULL, pexcl, t);
+            bool mine = i >= icarry && i < round_end && i < BLOCK && i >= kb && i < kb + kn;
+            if (mine) {
+                const uint32_t c = type_count(ktype), w = type_width(ktype), rel = i - kb;
+                const uint32_t r = rel / c, v = rel - r * c;
+                const uint32_t addr = p0 + kp + r * type_bytes(ktype);
+                uint32_t val;
+                if (ktype == 0) val = 1u;                                            // "0 bits" decodes to 1 (:129-133,657-660)
+                else if (ktype == 8) val = lds_u8(win, addr + v);
+                else if (ktype == 12) val = lds_u32(win, addr + 2u * v) & 0xffffu;
+                else if (ktype == 14) val = lds_u32(win, addr + 4u * v);
+                else {
+                    const uint32_t l = v & 3u, row = v >> 2;
+                    const uint32_t mask = (1u << w) - 1u;
+                    const uint32_t lo = lds_u32(win, addr + 4u * l);
+                    if (ktype == 7 || ktype == 9 || ktype == 11 || ktype == 13) {
+                        const uint32_t hi = lds_u32(win, addr + 16u + 4u * l);
+                        const uint32_t rs = 32u / w;                                 // the straddling row
+                        const uint32_t resume = ktype == 7 ? 3u : ktype == 9 ? 4u : ktype == 11 ? 8u : 11u;
+                        if (row < rs) val = (lo >> (row * w)) & mask;
+                        else if (row == rs) val = ((lo >> (rs * w)) | (hi << (32u - rs * w))) & mask;
+                        else val = (hi >> (resume + w * (row - rs - 1u))) & mask;
+                    } else {
+                        val = (lo >> (row * w)) & mask;
+                    }
+                }
+                out[i] = val;
+            }
+        }
+        pcarry += __shfl_sync(FULL, pincl, 31);
+        icarry = round_end;
+        if (nvalid < 32u) break;
+    }
+    __syncwarp();
+    return (p0 - off) + len;
 }
 
 // ---- Binary interpolative block, n <= 128 (interpolative_coding.hpp:93-146) -------------------

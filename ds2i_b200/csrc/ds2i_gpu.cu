@@ -154,8 +154,6 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
     int kind;
     int codec = codec_from_type(index_type, &kind);
     if (codec < 0) return fail(DS2I_E_UNSUPPORTED, std::string("unsupported index type ") + index_type);
-    if (kind == KIND_BLOCK && (codec == CODEC_VARINT || codec == CODEC_QMX))
-        return fail(DS2I_E_UNSUPPORTED, std::string("index type not built yet: ") + index_type);
     CUDA_TRY(cudaSetDevice(device));
     std::unique_ptr<ds2i_gpu_index> ix(new ds2i_gpu_index);
     ix->device = device; ix->kind = kind; ix->codec = codec;
@@ -195,7 +193,7 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
         CUDA_TRY(cudaMemset(ix->d_lists.p + f.lists_bytes, 0, pad));
         CUDA_TRY(ix->d_dir.upload(ix->host_dir));
         ix->dev.lists = ix->d_lists.p; ix->dev.dir = ix->d_dir.p;
-        ix->dev.num_lists = f.size; ix->dev.num_docs = uint32_t(f.num_docs);
+        ix->dev.num_lists = f.size; ix->dev.num_docs = uint32_t(f.num_docs); ix->dev.codec = codec;
         ix->device_bytes = f.lists_bytes + pad + f.size * sizeof(ListDir);
     } catch (std::exception const& e) {
         return fail(DS2I_E_FORMAT, e.what());
@@ -490,18 +488,12 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
         if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND)) {
             if (!ranked) k = 1;
-            if (ix->codec == CODEC_OPTPFOR) rc = op == OP_AND ? launch_and_block<CODEC_OPTPFOR, false>(b, db, k) : launch_and_block<CODEC_OPTPFOR, true>(b, db, k);
-            else if (ix->codec == CODEC_INTERPOLATIVE) rc = op == OP_AND ? launch_and_block<CODEC_INTERPOLATIVE, false>(b, db, k) : launch_and_block<CODEC_INTERPOLATIVE, true>(b, db, k);
-            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+            rc = op == OP_AND ? launch_and_block<CODEC_ANY, false>(b, db, k) : launch_and_block<CODEC_ANY, true>(b, db, k);
         }
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE)) {
-            if (ix->codec == CODEC_OPTPFOR) rc = launch_union_block<CODEC_OPTPFOR>(b, db, k);
-            else if (ix->codec == CODEC_INTERPOLATIVE) rc = launch_union_block<CODEC_INTERPOLATIVE>(b, db, k);
-            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+            rc = launch_union_block<CODEC_ANY>(b, db, k);
         }
-        else if (ix->codec == CODEC_OPTPFOR) rc = launch_query_op<CODEC_OPTPFOR>(b, db, op, k);
-        else if (ix->codec == CODEC_INTERPOLATIVE) rc = launch_query_op<CODEC_INTERPOLATIVE>(b, db, op, k);
-        else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+        else rc = launch_query_op<CODEC_ANY>(b, db, op, k);
         if (rc != DS2I_OK) return rc;
         b->launches += 1;
     }
@@ -594,7 +586,7 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, Decode
     uint32_t* scratch = stage + STAGE_WORDS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
     WarpCtx c;
-    ctx_init(c, stage, scratch, bar);
+    ctx_init(c, stage, scratch, bar, idx.codec);
 
     const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
     for (uint64_t g = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp; g < job.total_blocks; g += nwarps) {
@@ -659,9 +651,7 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
             uint64_t want = (blk[nterms] + 7) / 8;
             int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
-            if (ix->codec == CODEC_OPTPFOR) decode_blocks_kernel<CODEC_OPTPFOR><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
-            else if (ix->codec == CODEC_INTERPOLATIVE) decode_blocks_kernel<CODEC_INTERPOLATIVE><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
-            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+            decode_blocks_kernel<CODEC_ANY><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
         }
     }
     CUDA_TRY(cudaEventRecord(e1));
@@ -701,7 +691,7 @@ __global__ void __launch_bounds__(128) next_geq_kernel(DevIndex idx, GeqJob job)
     uint32_t* scratch = stage + STAGE_WORDS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
     WarpCtx c;
-    ctx_init(c, stage, scratch, bar);
+    ctx_init(c, stage, scratch, bar, idx.codec);
     while (true) {
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(job.work_counter, 1u);
@@ -743,9 +733,7 @@ extern "C" int ds2i_gpu_next_geq_batch(ds2i_gpu_index* ix, const uint32_t* terms
         } else {
             GeqJob job{d_terms.p, d_bounds.p, d_offs.p, d_docids.p, d_freqs.p, d_counter.p, uint32_t(nlists)};
             int grid = int(std::min<uint64_t>((nlists + 3) / 4, uint64_t(ix->sm_count) * 8));
-            if (ix->codec == CODEC_OPTPFOR) next_geq_kernel<CODEC_OPTPFOR><<<grid, 128, S16_TAB_BYTES + 4 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
-            else if (ix->codec == CODEC_INTERPOLATIVE) next_geq_kernel<CODEC_INTERPOLATIVE><<<grid, 128, S16_TAB_BYTES + 4 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
-            else rc = fail(DS2I_E_UNSUPPORTED, "codec not built");
+            next_geq_kernel<CODEC_ANY><<<grid, 128, S16_TAB_BYTES + 4 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
         }
     }
     CUDA_TRY(cudaEventRecord(e1));

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) query_kernel(DevIndex idx, DevWand wand, 
     uint32_t* scratch = stage + STAGE_WORDS;
 
     WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar);
+    ctx_init(c, stage, scratch, &ws->bar, idx.codec);
     const uint32_t N = idx.num_docs;
     constexpr bool RANKED = (OP == OP_RANKED_AND || OP == OP_WAND || OP == OP_MAXSCORE || OP == OP_RANKED_OR);
 

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
     uint32_t* scratch = stage + STAGE_WORDS;
 
     WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar);
+    ctx_init(c, stage, scratch, &ws->bar, idx.codec);
 
     while (true) {
         uint32_t ii = 0;

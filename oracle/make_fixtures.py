@@ -112,7 +112,7 @@ def main():
     with open(mqp, "w") as g:
         for q in mq:
             g.write("\t".join(str(t) for t in q) + "\n")
-    build_all(tmp, os.path.join(GOLDEN, "mini"), ["block_optpfor", "block_interpolative", "opt"], mqp)
+    build_all(tmp, os.path.join(GOLDEN, "mini"), ["block_optpfor", "block_interpolative", "block_varint", "block_qmx", "opt"], mqp)
     np.savez_compressed(os.path.join(GOLDEN, "mini.collection.npz"), num_docs=np.uint64(num_docs),
                         lens=np.array([len(docs[t]) for t in terms], dtype=np.uint64),
                         docs=np.concatenate([docs[t] for t in terms]), freqs=np.concatenate([freqs[t] for t in terms]),
