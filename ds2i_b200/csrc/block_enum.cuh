@@ -119,6 +119,8 @@ __device__ __forceinline__ uint32_t decode_values(WarpCtx& c, uint32_t off, uint
 
 template <int CODEC>
 struct BlockEnum {
+    typedef ListState State;
+    typedef DevIndex Index;
     // document_enumerator ctor + reset(): block_posting_list.hpp:86-108
     static __device__ __forceinline__ void open(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t term) {
         ListDir d = idx.dir[term];

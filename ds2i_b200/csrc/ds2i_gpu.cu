@@ -646,7 +646,7 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
     int rc = DS2I_OK;
     if (nterms && total) {
         if (ix->kind == KIND_PEF) {
-            rc = pef_decode_lists(*ix->pef, d_terms.p, uint32_t(nterms), d_offs.p, d_docs.p, d_freqs.p, ix->sm_count, g_last_error);
+            rc = pef_decode_lists(*ix->pef, terms, d_terms.p, uint32_t(nterms), d_offs.p, d_docs.p, d_freqs.p, ix->sm_count, g_last_error);
         } else {
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
             uint64_t want = (blk[nterms] + 7) / 8;

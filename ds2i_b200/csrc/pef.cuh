@@ -1,0 +1,298 @@
+// Device side of ds2i's partitioned Elias-Fano index (`opt`): freq_index<partitioned_sequence<>,
+// positive_sequence<partitioned_sequence<strict_sequence>>> (index_types.hpp:30-33).
+//
+// The two big bit vectors (docs, freqs) are copied into HBM as they are on disk (64-bit words,
+// LSB-first).  What the reference re-derives on every partition switch — partition sizes,
+// upper bounds and endpoints, each an Elias-Fano / fixed-width sequence in the list header
+// (partitioned_sequence.hpp:299-326) — is decoded ONCE at load time into a flat partition directory
+// (PefPart), the analogue of block_maxs/block_endpoints of the block indexes, so that a warp finds a
+// partition with the same ballot search it uses for block_max.  Partition bodies stay compressed and
+// are decoded on the fly, 128 consecutive elements at a time ("chunk"):
+//   * compact_elias_fano body (compact_elias_fano.hpp:14-61,105-126): the set bits of the high-bits
+//     region are located 32 words per step (popcount + warp scan + select-in-word), starting from the
+//     pointers1 sample of the chunk; low bits come from one unaligned field read per element;
+//   * compact_ranked_bitvector body (compact_ranked_bitvector.hpp:14-50): same scan over the bitmap;
+//   * all_ones (all_ones_sequence.hpp): arithmetic.
+// next_geq inside a large partition uses pointers0 (EF, :291-336) / rank1 samples (bitvector).
+#pragma once
+#include "device_common.cuh"
+
+namespace ds2i_gpu {
+
+struct PefPart {            // one partition of one sequence
+    uint64_t bit_off;       // absolute bit offset of the partition body (its type bit, when present)
+    uint32_t begin;         // position of its first element inside the list
+    uint32_t size;          // elements
+    uint32_t base;          // value offset: stored values are relative to it
+    uint32_t ub;            // its last value (absolute)
+};
+
+struct PefListDir {
+    uint64_t first_part;    // index into the PefPart array
+    uint32_t nparts;
+    uint32_t n;             // elements of the sequence
+};
+
+struct PefSeq {             // one bitvector_collection on device
+    const uint64_t* bits;   // m_bitvectors words, 8-byte aligned copy with a zero tail
+    const PefListDir* lists;
+    const PefPart* parts;
+    uint32_t log_sampling0, log_sampling1, rb_log_rank1_sampling, rb_log_sampling1;
+};
+
+struct PefIndexDev {
+    PefSeq docs, freqs;
+    uint64_t num_lists;
+    uint32_t num_docs;
+};
+
+enum : uint32_t { PEF_EF = 0, PEF_RB = 1, PEF_AO = 2 };
+
+__device__ __forceinline__ uint32_t ceil_log2_dev(uint64_t x) { return x > 1 ? 64u - uint32_t(__clzll(x - 1)) : 0u; }
+
+// bits [pos, pos+len) of the vector, len <= 32
+__device__ __forceinline__ uint32_t bv_get_bits(const uint64_t* bits, uint64_t pos, uint32_t len) {
+    if (!len) return 0u;
+    uint64_t w = __ldg(bits + (pos >> 6));
+    uint32_t sh = uint32_t(pos & 63);
+    uint64_t v = w >> sh;
+    if (sh + len > 64) v |= __ldg(bits + (pos >> 6) + 1) << (64 - sh);
+    return uint32_t(v) & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u));
+}
+__device__ __forceinline__ uint64_t bv_get_bits64(const uint64_t* bits, uint64_t pos, uint32_t len) {   // len <= 57
+    if (!len) return 0ull;
+    uint64_t w = __ldg(bits + (pos >> 6));
+    uint32_t sh = uint32_t(pos & 63);
+    uint64_t v = w >> sh;
+    if (sh + len > 64) v |= __ldg(bits + (pos >> 6) + 1) << (64 - sh);
+    return v & ((uint64_t(1) << len) - 1);
+}
+
+// k-th (0-based) set bit of a 64-bit word
+__device__ __forceinline__ uint32_t select_in_word(uint64_t w, uint32_t k) {
+    uint32_t lo = uint32_t(w), hi = uint32_t(w >> 32);
+    uint32_t pl = __popc(lo);
+    if (k < pl) return __fns(lo, 0, int(k) + 1);
+    return 32u + __fns(hi, 0, int(k - pl) + 1);
+}
+
+// Layout of one partition body, resolved from (universe, n) like the reference constructors do.
+struct PefBody {
+    uint32_t type;
+    uint32_t n, universe;
+    uint32_t lower_bits;        // EF
+    uint32_t pointer_size;
+    uint64_t pointers0_off, pointers1_off, high_off, low_off;       // EF (absolute bit offsets)
+    uint64_t rank_off, rb_ptr1_off, bitmap_off;                     // RB
+    uint32_t rank_sample_size, n_rank_samples;
+    uint32_t log_s0, log_s1;
+    bool strict;                // strict_elias_fano: stored value = v - i over universe - n + 1
+};
+
+// indexed_sequence / strict_sequence dispatch (indexed_sequence.hpp:95-127, strict_sequence.hpp:104-137)
+__device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart const& p, bool strict) {
+    PefBody b;
+    b.n = p.size;
+    b.universe = p.ub - p.base + 1u;            // last relative value + 1
+    b.strict = strict;
+    if (b.universe == b.n) { b.type = PEF_AO; return b; }
+    b.type = uint32_t(__ldg(seq.bits + (p.bit_off >> 6)) >> (p.bit_off & 63)) & 1u;
+    const uint64_t off = p.bit_off + 1;
+    if (b.type == PEF_EF) {
+        // strict variants never index zeros (strict_sequence.hpp:24-30: ef_log_sampling0 = 63)
+        b.log_s0 = strict ? 63u : seq.log_sampling0;
+        b.log_s1 = seq.log_sampling1;
+        uint64_t u = strict ? uint64_t(b.universe) - b.n + 1 : uint64_t(b.universe);
+        uint64_t n = b.n;
+        b.lower_bits = u > n ? 63u - uint32_t(__clzll(u / n)) : 0u;
+        uint64_t hbl = n + (u >> b.lower_bits) + 2;
+        b.pointer_size = ceil_log2_dev(hbl);
+        uint64_t p0 = b.log_s0 >= 63 ? 0 : ((hbl - n) >> b.log_s0);
+        uint64_t p1 = n >> b.log_s1;
+        b.pointers0_off = off;
+        b.pointers1_off = off + p0 * b.pointer_size;
+        b.high_off = b.pointers1_off + p1 * b.pointer_size;
+        b.low_off = b.high_off + hbl;
+    } else {
+        b.log_s0 = strict ? 63u : seq.rb_log_rank1_sampling;
+        b.log_s1 = seq.rb_log_sampling1;
+        b.rank_sample_size = ceil_log2_dev(uint64_t(b.n) + 1);
+        b.pointer_size = ceil_log2_dev(b.universe);
+        b.n_rank_samples = b.log_s0 >= 63 ? 0u : (b.universe >> b.log_s0);
+        uint64_t p1 = b.n >> b.log_s1;
+        b.rank_off = off;
+        b.rb_ptr1_off = off + uint64_t(b.n_rank_samples) * b.rank_sample_size;
+        b.bitmap_off = b.rb_ptr1_off + p1 * b.pointer_size;
+    }
+    return b;
+}
+
+// Positions (relative to `origin`) of the set bits with ordinals r0 .. r0+cnt-1 (ordinal 0 = first
+// set bit at or after `start`), cnt <= 128, written to out[0..cnt).  32 words per step.
+__device__ __forceinline__ void pef_scan_ones(const uint64_t* bits, uint64_t start, uint64_t origin, uint32_t r0, uint32_t cnt, uint32_t* out) {
+    const unsigned lane = lane_id();
+    uint64_t wbase = start >> 6;
+    uint32_t seen = 0;                    // set bits before the words of this step
+    const uint32_t r1 = r0 + cnt;
+    bool first = true;
+    while (seen < r1) {
+        uint64_t w = __ldg(bits + wbase + lane);
+        if (first && lane == 0) w &= ~uint64_t(0) << (start & 63);
+        first = false;
+        uint32_t pc = __popcll(w);
+        uint32_t incl = warp_inclusive_scan(pc);
+        uint32_t excl = seen + incl - pc;
+        uint32_t total = seen + __shfl_sync(FULL, incl, 31);
+        // every lane looks for "its" outputs among the words of this step
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t o = r0 + lane + 32u * j;            // ordinal wanted
+            bool want = (lane + 32u * j) < cnt && o >= seen && o < total;
+            uint32_t t = 0;                               // word holding ordinal o: largest t with excl_t <= o
+#pragma unroll
+            for (uint32_t s = 16; s >= 1; s >>= 1) {
+                uint32_t e = __shfl_sync(FULL, excl, (t + s) & 31u);
+                if (e <= o) t += s;
+            }
+            // words with no set bits share excl with their successor; the search lands on the last such
+            // word, which is the one that owns the ordinal when it has bits — walk back is not needed
+            // because an empty word's excl equals the next word's excl and the search prefers the later one.
+            uint32_t we = __shfl_sync(FULL, excl, t);
+            uint32_t wlo = __shfl_sync(FULL, uint32_t(w), t), whi = __shfl_sync(FULL, uint32_t(w >> 32), t);
+            if (want) {
+                uint64_t ww = (uint64_t(whi) << 32) | wlo;
+                uint32_t bit = select_in_word(ww, o - we);
+                out[lane + 32u * j] = uint32_t((wbase + t) * 64 + bit - origin);
+            }
+        }
+        seen = total;
+        wbase += 32;
+    }
+    __syncwarp();
+}
+
+// count of ZERO bits wanted: position (relative to origin) of the zero with ordinal z (0 = first zero
+// at or after start), z < 2^log_sampling0 + slack.  Returns warp-uniformly.
+__device__ __forceinline__ uint64_t pef_select_zero(const uint64_t* bits, uint64_t start, uint32_t z) {
+    const unsigned lane = lane_id();
+    uint64_t wbase = start >> 6;
+    uint32_t seen = 0;
+    bool first = true;
+    while (true) {
+        uint64_t w = ~__ldg(bits + wbase + lane);
+        if (first && lane == 0) w &= ~uint64_t(0) << (start & 63);
+        first = false;
+        uint32_t pc = __popcll(w);
+        uint32_t incl = warp_inclusive_scan(pc);
+        uint32_t excl = seen + incl - pc;
+        unsigned hit = __ballot_sync(FULL, z >= excl && z < excl + pc);
+        if (hit) {
+            uint32_t t = __ffs(hit) - 1;
+            uint32_t e = __shfl_sync(FULL, excl, t);
+            uint32_t wlo = __shfl_sync(FULL, uint32_t(w), t), whi = __shfl_sync(FULL, uint32_t(w >> 32), t);
+            uint32_t bit = select_in_word((uint64_t(whi) << 32) | wlo, z - e);
+            return (wbase + t) * 64 + bit;
+        }
+        seen += __shfl_sync(FULL, incl, 31);
+        wbase += 32;
+    }
+}
+
+// Elements [i0, i0+cnt) of a partition (cnt <= 128) as ABSOLUTE values (base added) into out[0..cnt).
+__device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out) {
+    const unsigned lane = lane_id();
+    if (b.type == PEF_AO) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t e = lane + 32u * j;
+            if (e < cnt) out[e] = p.base + i0 + e;
+        }
+        __syncwarp();
+        return;
+    }
+    const uint32_t s = i0 >> b.log_s1;                     // pointers1 sample at or before i0
+    if (b.type == PEF_EF) {
+        uint64_t start = b.high_off;
+        uint32_t r0 = i0;
+        if (s) {
+            uint64_t ptr = bv_get_bits64(seq.bits, b.pointers1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
+            start = b.high_off + ptr;                      // high-bit position of element s << log_s1
+            r0 = i0 - (s << b.log_s1);
+        }
+        pef_scan_ones(seq.bits, start, b.high_off, r0, cnt, out);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t e = lane + 32u * j;
+            if (e < cnt) {
+                uint32_t i = i0 + e;
+                uint32_t high = out[e] - i - 1u;
+                uint32_t low = bv_get_bits(seq.bits, b.low_off + uint64_t(i) * b.lower_bits, b.lower_bits);
+                uint32_t v = (high << b.lower_bits) | low;
+                if (b.strict) v += i;                      // strict_elias_fano.hpp:50-60
+                out[e] = p.base + v;
+            }
+        }
+    } else {
+        uint64_t start = b.bitmap_off;
+        uint32_t r0 = i0;
+        if (s) {
+            uint64_t ptr = bv_get_bits64(seq.bits, b.rb_ptr1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
+            start = b.bitmap_off + ptr;                    // value of element s << log_s1 = its bit position
+            r0 = i0 - (s << b.log_s1);
+        }
+        pef_scan_ones(seq.bits, start, b.bitmap_off, r0, cnt, out);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t e = lane + 32u * j;
+            if (e < cnt) out[e] = p.base + out[e];
+        }
+    }
+    __syncwarp();
+}
+
+// Index of the first element whose high part is >= (x >> l) (EF) / whose value is >= x (bitvector,
+// all-ones): a lower bound for the rank of x; for EF the caller refines by comparing decoded values.
+// x is relative to the partition base, x < universe.
+__device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody const& b, uint32_t x) {
+    if (b.type == PEF_AO) return x;
+    if (b.type == PEF_EF) {
+        uint32_t high = x >> b.lower_bits;
+        if (high == 0) return 0;
+        // position of the zero that has `high` zeros before it (compact_elias_fano.hpp:291-336)
+        uint32_t k = b.log_s0 >= 63 ? 0u : (high >> b.log_s0);
+        uint64_t start = b.high_off;
+        uint32_t skip = high;
+        if (k) {
+            uint64_t ptr = bv_get_bits64(seq.bits, b.pointers0_off + uint64_t(k - 1) * b.pointer_size, b.pointer_size);
+            start = b.high_off + ptr;
+            skip = high - (k << b.log_s0);
+        }
+        uint64_t z = pef_select_zero(seq.bits, start, skip);
+        return uint32_t(z - b.high_off) - high;
+    }
+    // ranked bitvector: ones in [0, x) = sample + popcount of the remainder (compact_ranked_bitvector.hpp:256-302)
+    const unsigned lane = lane_id();
+    uint32_t k = b.log_s0 >= 63 ? 0u : (x >> b.log_s0);
+    if (k > b.n_rank_samples) k = b.n_rank_samples;
+    uint32_t rank = 0;
+    uint64_t from = b.bitmap_off;
+    if (k) {
+        rank = uint32_t(bv_get_bits64(seq.bits, b.rank_off + uint64_t(k - 1) * b.rank_sample_size, b.rank_sample_size));
+        from = b.bitmap_off + (uint64_t(k) << b.log_s0);
+    }
+    const uint64_t to = b.bitmap_off + x;
+    uint32_t acc = 0;
+    for (uint64_t wb = from >> 6; wb * 64 < to; wb += 32) {
+        uint64_t wi = wb + lane;
+        uint64_t w = 0;
+        if (wi * 64 < to) {
+            w = __ldg(seq.bits + wi);
+            if (wi == (from >> 6)) w &= ~uint64_t(0) << (from & 63);
+            if ((wi + 1) * 64 > to) w &= (uint64_t(1) << (to & 63)) - 1;
+        }
+        acc += __popcll(w);
+    }
+    return rank + __reduce_add_sync(FULL, acc);
+}
+
+}  // namespace ds2i_gpu

@@ -1,21 +1,505 @@
-// Partitioned Elias-Fano (opt_index) device path — placeholder until the PEF enumerator lands.
+// Partitioned Elias-Fano (`opt` index) path: host-side loader that flattens the per-list partition
+// headers into a directory, the device enumerator with ds2i's next / next_geq / docid / freq
+// semantics (freq_index.hpp:116-190, partitioned_sequence.hpp:122-347, positive_sequence.hpp:33-78),
+// and the kernels behind decode_lists / next_geq_batch / the query operators for this index type.
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
+
+#include "format.hpp"
+#include "pef.cuh"
 #include "query_kernels.cuh"
 
 namespace ds2i_gpu {
 
-struct PefListDir { uint64_t n; };
+// ------------------------------------------------------------------------------------------------
+// device enumerator
+
+struct PefState {
+    // docs sequence
+    uint64_t d_first_part;
+    uint32_t d_nparts, n;
+    uint32_t cur_part;          // index of the current docs partition inside the list
+    uint32_t chunk_i0;          // local index (inside the partition) of docs[0]
+    uint32_t chunk_size;
+    uint32_t pos;               // position inside the chunk
+    uint32_t cur_docid;
+    uint32_t part_begin;        // list position of the partition's first element
+    // freqs sequence
+    uint64_t f_first_part;
+    uint32_t f_nparts;
+    uint32_t f_cur_part;
+    uint32_t f_g0;              // list position of fvals[0]
+    uint32_t f_cnt;             // valid entries in fvals (0 = nothing cached)
+    uint32_t f_prev0;           // prefix-sum value just before fvals[0] (valid when f_has_prev)
+    uint32_t f_has_prev;
+    uint32_t pad[2];
+    uint32_t docs[128];         // docids of the current chunk (0xffffffff beyond chunk_size)
+    uint32_t fvals[128];        // prefix sums of freqs for list positions f_g0 ..
+};
+static_assert(sizeof(PefState) % 16 == 0, "PefState must keep 16-byte alignment of its arrays");
+
+struct PefEnum {
+    typedef PefState State;
+    typedef PefIndexDev Index;
+
+    static __device__ __forceinline__ PefPart load_part(const PefPart* parts, uint64_t i) {
+        PefPart r;
+        const uint64_t* q = reinterpret_cast<const uint64_t*>(parts + i);       // 24-byte records, 8-byte aligned
+        r.bit_off = __ldg(q);
+        uint64_t a = __ldg(q + 1), b = __ldg(q + 2);
+        r.begin = uint32_t(a); r.size = uint32_t(a >> 32); r.base = uint32_t(b); r.ub = uint32_t(b >> 32);
+        return r;
+    }
+
+    // decode the chunk of partition `part` that starts at local index i0
+    static __device__ __forceinline__ void load_chunk(Index const& idx, State* st, uint32_t part, uint32_t i0) {
+        PefPart p = load_part(idx.docs.parts, st->d_first_part + part);
+        PefBody b = pef_open_body(idx.docs, p, false);
+        uint32_t cnt = min(128u, p.size - i0);
+        pef_decode_range(idx.docs, p, b, i0, cnt, st->docs);
+        const unsigned lane = lane_id();
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) { uint32_t e = lane + 32u * j; if (e >= cnt) st->docs[e] = 0xffffffffu; }
+        __syncwarp();
+        if (lane == 0) {
+            st->cur_part = part; st->chunk_i0 = i0; st->chunk_size = cnt; st->pos = 0; st->part_begin = p.begin;
+            st->cur_docid = st->docs[0];
+        }
+        __syncwarp();
+    }
+
+    static __device__ __forceinline__ void open(WarpCtx&, Index const& idx, State* st, uint32_t term) {
+        if (lane_id() == 0) {
+            PefListDir d = idx.docs.lists[term], f = idx.freqs.lists[term];
+            st->d_first_part = d.first_part; st->d_nparts = d.nparts; st->n = d.n;
+            st->f_first_part = f.first_part; st->f_nparts = f.nparts; st->f_cur_part = 0; st->f_cnt = 0; st->f_g0 = 0;
+            st->f_has_prev = 0; st->f_prev0 = 0;
+        }
+        __syncwarp();
+        load_chunk(idx, st, 0, 0);
+    }
+
+    static __device__ __forceinline__ uint32_t docid(const State* st) { return st->cur_docid; }
+    static __device__ __forceinline__ uint32_t size(const State* st) { return st->n; }
+    static __device__ __forceinline__ uint64_t position(const State* st) { return uint64_t(st->part_begin) + st->chunk_i0 + st->pos; }
+
+    static __device__ __forceinline__ uint32_t set_end(Index const& idx, State* st) {
+        __syncwarp();
+        if (lane_id() == 0) { st->cur_docid = idx.num_docs; st->pos = st->chunk_size; }
+        __syncwarp();
+        return idx.num_docs;
+    }
+
+    static __device__ __forceinline__ uint32_t next(WarpCtx&, Index const& idx, State* st) {
+        uint32_t pos = st->pos + 1;
+        if (pos < st->chunk_size) {
+            uint32_t d = st->docs[pos];
+            __syncwarp();
+            if (lane_id() == 0) { st->pos = pos; st->cur_docid = d; }
+            __syncwarp();
+            return d;
+        }
+        // next chunk of the partition, or the next partition, or the end (partitioned_sequence.hpp:236-250)
+        PefPart p = load_part(idx.docs.parts, st->d_first_part + st->cur_part);
+        uint32_t ni = st->chunk_i0 + st->chunk_size;
+        if (ni < p.size) { load_chunk(idx, st, st->cur_part, ni); return st->cur_docid; }
+        if (st->cur_part + 1 < st->d_nparts) { load_chunk(idx, st, st->cur_part + 1, 0); return st->cur_docid; }
+        return set_end(idx, st);
+    }
+
+    // first posting with docid >= lower_bound at or after the cursor (the block-list semantics; the
+    // reference's EF enumerators agree with it for non-decreasing bounds)
+    static __device__ __forceinline__ uint32_t next_geq(WarpCtx&, Index const& idx, State* st, uint32_t lower_bound) {
+        const unsigned lane = lane_id();
+        const uint32_t cur = st->cur_docid;
+        if (cur == idx.num_docs || cur >= lower_bound) return cur;
+        uint32_t chunk_last = st->docs[st->chunk_size - 1];
+        if (lower_bound > chunk_last) {
+            uint32_t part = st->cur_part;
+            PefPart p = load_part(idx.docs.parts, st->d_first_part + part);
+            if (lower_bound > p.ub) {
+                // partition search on the flattened upper bounds (the reference: m_upper_bounds.next_geq, :286)
+                const uint32_t nparts = st->d_nparts;
+                uint32_t lo = part + 1;
+                bool found = false;
+                while (lo < nparts) {
+                    uint32_t pi = lo + lane;
+                    uint32_t ub = 0;
+                    if (pi < nparts) ub = uint32_t(__ldg(reinterpret_cast<const uint64_t*>(idx.docs.parts + st->d_first_part + pi) + 2) >> 32);
+                    unsigned hit = __ballot_sync(FULL, pi < nparts && ub >= lower_bound);
+                    if (hit) { lo += __ffs(hit) - 1; found = true; break; }
+                    lo += 32;
+                }
+                if (!found) return set_end(idx, st);
+                part = lo;
+                p = load_part(idx.docs.parts, st->d_first_part + part);
+                if (lower_bound <= p.base) { load_chunk(idx, st, part, 0); return st->cur_docid; }
+            }
+            // inside partition `part`: locate the chunk holding the first value >= lower_bound
+            PefBody b = pef_open_body(idx.docs, p, false);
+            uint32_t from = (part == st->cur_part) ? st->chunk_i0 + st->chunk_size : 0u;
+            uint32_t i0 = from;
+            if (p.size - from > 128u) {
+                uint32_t hint = pef_rank_hint(idx.docs, b, lower_bound - p.base);
+                if (hint > i0) i0 = hint;
+                if (i0 >= p.size) i0 = p.size - 1;      // lower_bound <= ub: the last element qualifies
+            }
+            while (true) {
+                load_chunk(idx, st, part, i0);
+                if (st->docs[st->chunk_size - 1] >= lower_bound) break;
+                i0 += st->chunk_size;                   // (EF: elements sharing the high part of the bound may span chunks)
+            }
+        }
+        uint4 v = reinterpret_cast<const uint4*>(st->docs)[lane];
+        uint32_t cnt = (v.x < lower_bound) + (v.y < lower_bound) + (v.z < lower_bound) + (v.w < lower_bound);
+        uint32_t pos = __reduce_add_sync(FULL, cnt);
+        uint32_t cp = st->pos;
+        if (pos < cp) pos = cp;
+        uint32_t d = st->docs[pos & 127u];
+        __syncwarp();
+        if (lane == 0) { st->pos = pos; st->cur_docid = d; }
+        __syncwarp();
+        return d;
+    }
+
+    // prefix sums of the freqs sequence for list positions starting at max(g - 1, partition begin)
+    static __device__ __forceinline__ void load_freq_chunk(Index const& idx, State* st, uint32_t g) {
+        const unsigned lane = lane_id();
+        // partition of the freqs sequence that holds position g
+        uint32_t fp = st->f_cur_part;
+        const uint32_t nparts = st->f_nparts;
+        PefPart p = load_part(idx.freqs.parts, st->f_first_part + fp);
+        if (g < p.begin) { fp = 0; p = load_part(idx.freqs.parts, st->f_first_part); }
+        while (g >= p.begin + p.size) {
+            // forward scan, 32 partitions per step
+            uint32_t pi = fp + 1 + lane;
+            uint32_t end = 0;
+            if (pi < nparts) {
+                uint64_t a = __ldg(reinterpret_cast<const uint64_t*>(idx.freqs.parts + st->f_first_part + pi) + 1);
+                end = uint32_t(a) + uint32_t(a >> 32);
+            }
+            unsigned hit = __ballot_sync(FULL, pi < nparts && g < end);
+            if (hit) fp = fp + 1 + (__ffs(hit) - 1); else fp += 32;
+            if (fp >= nparts) fp = nparts - 1;
+            p = load_part(idx.freqs.parts, st->f_first_part + fp);
+            if (hit) break;
+        }
+        PefBody b = pef_open_body(idx.freqs, p, true);
+        uint32_t local = g - p.begin;
+        uint32_t ls = local ? local - 1 : 0;
+        uint32_t cnt = min(128u, p.size - ls);
+        pef_decode_range(idx.freqs, p, b, ls, cnt, st->fvals);
+        if (lane == 0) {
+            st->f_cur_part = fp; st->f_g0 = p.begin + ls; st->f_cnt = cnt;
+            st->f_has_prev = (ls == 0) ? 1u : 0u;
+            // the value before a partition's first element is the previous partition's last value = base - 1
+            // (partition 0: base is the first value itself and the sum before it is 0)
+            st->f_prev0 = (ls == 0 && fp) ? p.base - 1u : 0u;
+        }
+        __syncwarp();
+    }
+
+    // positive_sequence::enumerator::move(position).second (positive_sequence.hpp:48-66)
+    static __device__ __forceinline__ uint32_t freq(WarpCtx&, Index const& idx, State* st) {
+        const uint32_t g = st->part_begin + st->chunk_i0 + st->pos;
+        bool ok = st->f_cnt && g >= st->f_g0 && g < st->f_g0 + st->f_cnt && (g > st->f_g0 || st->f_has_prev);
+        if (!ok) load_freq_chunk(idx, st, g);
+        uint32_t j = g - st->f_g0;
+        uint32_t cur = st->fvals[j];
+        uint32_t prev = j ? st->fvals[j - 1] : st->f_prev0;
+        return cur - prev;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+
+// the reference's operators, literally, over the PEF enumerator (same control flow as query_kernel)
+template <int OP>
+__global__ void __launch_bounds__(128) pef_query_kernel(PefIndexDev idx, DevWand wand, DevBatch batch, uint32_t k, int slots) {
+    run_queries<PefEnum, OP>(idx, wand, batch, k, slots, 0);
+}
+
+struct PefDecodeJob {
+    const uint32_t* terms;
+    const uint64_t* part_prefix;   // nterms+1: (docs partitions + freqs partitions) before list i
+    const uint64_t* out_offsets;
+    uint32_t* out_docs;
+    uint32_t* out_freqs;
+    uint64_t total_parts;
+    uint32_t nterms;
+};
+
+// full decode: one warp per partition (docs partitions first, then freqs partitions of each list)
+static __global__ void __launch_bounds__(256) pef_decode_kernel(PefIndexDev idx, PefDecodeJob job) {
+    uint32_t* buf = smem_words((threadIdx.x >> 5) * 512);
+    const unsigned lane = lane_id();
+    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
+    for (uint64_t g = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); g < job.total_parts; g += nwarps) {
+        uint32_t lo = 0, hi = job.nterms;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (job.part_prefix[mid] <= g) lo = mid; else hi = mid; }
+        const uint32_t term = job.terms[lo];
+        uint32_t pi = uint32_t(g - job.part_prefix[lo]);
+        const PefListDir d = idx.docs.lists[term], f = idx.freqs.lists[term];
+        const uint64_t o = job.out_offsets[lo];
+        if (pi < d.nparts) {
+            PefPart p = PefEnum::load_part(idx.docs.parts, d.first_part + pi);
+            PefBody b = pef_open_body(idx.docs, p, false);
+            for (uint32_t i0 = 0; i0 < p.size; i0 += 128) {
+                uint32_t cnt = min(128u, p.size - i0);
+                pef_decode_range(idx.docs, p, b, i0, cnt, buf);
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) { uint32_t e = lane + 32u * j; if (e < cnt) job.out_docs[o + p.begin + i0 + e] = buf[e]; }
+                __syncwarp();
+            }
+        } else {
+            pi -= d.nparts;
+            PefPart p = PefEnum::load_part(idx.freqs.parts, f.first_part + pi);
+            PefBody b = pef_open_body(idx.freqs, p, true);
+            uint32_t prev = pi ? p.base - 1u : 0u;       // prefix sum before the partition's first element
+            for (uint32_t i0 = 0; i0 < p.size; i0 += 128) {
+                uint32_t cnt = min(128u, p.size - i0);
+                pef_decode_range(idx.freqs, p, b, i0, cnt, buf);
+                uint32_t last = buf[cnt - 1];
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) {
+                    uint32_t e = lane + 32u * j;
+                    if (e < cnt) job.out_freqs[o + p.begin + i0 + e] = buf[e] - (e ? buf[e - 1] : prev);
+                }
+                __syncwarp();
+                prev = last;
+            }
+        }
+    }
+}
+
+struct PefGeqJob {
+    const uint32_t* terms;
+    const uint64_t* bounds;
+    const uint64_t* bound_offsets;
+    uint64_t* out_docids;
+    uint64_t* out_freqs;
+    uint32_t* work_counter;
+    uint32_t nlists;
+};
+
+static __global__ void __launch_bounds__(128) pef_next_geq_kernel(PefIndexDev idx, PefGeqJob job) {
+    PefState* st = reinterpret_cast<PefState*>(g_smem + (threadIdx.x >> 5) * sizeof(PefState));
+    const unsigned lane = lane_id();
+    WarpCtx c;
+    c.c_docs_blocks = c.c_freqs_blocks = c.c_docs_bytes = c.c_freqs_bytes = c.c_maxs = c.c_scored = 0;
+    while (true) {
+        uint32_t li = 0;
+        if (lane == 0) li = atomicAdd(job.work_counter, 1u);
+        li = __shfl_sync(FULL, li, 0);
+        if (li >= job.nlists) break;
+        PefEnum::open(c, idx, st, job.terms[li]);
+        for (uint64_t j = job.bound_offsets[li]; j < job.bound_offsets[li + 1]; ++j) {
+            uint64_t lb = job.bounds[j];
+            uint32_t d = lb >= idx.num_docs ? PefEnum::next_geq(c, idx, st, idx.num_docs) : PefEnum::next_geq(c, idx, st, uint32_t(lb));
+            uint32_t f = d < idx.num_docs ? PefEnum::freq(c, idx, st) : 0u;
+            if (lane == 0) { job.out_docids[j] = d; job.out_freqs[j] = f; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: loader
+
+struct PefSeqHost {
+    std::vector<PefListDir> lists;
+    std::vector<PefPart> parts;
+    uint64_t* d_bits = nullptr;
+    PefListDir* d_lists = nullptr;
+    PefPart* d_parts = nullptr;
+    uint64_t device_bytes = 0;
+    ~PefSeqHost() { if (d_bits) cudaFree(d_bits); if (d_lists) cudaFree(d_lists); if (d_parts) cudaFree(d_parts); }
+};
+
+struct bit_cursor {          // succinct::bit_vector::enumerator subset
+    bitvec_view const& bv;
+    uint64_t pos;
+    uint64_t take(uint32_t len) { uint64_t v = get_bits(bv, pos, len); pos += len; return v; }
+    uint32_t skip_zeros() {
+        uint32_t z = 0;
+        while (true) {
+            if (pos >= bv.bits) throw format_error("gamma code runs past the bit vector");
+            if (get_bits(bv, pos, 1)) { ++pos; return z; }
+            ++pos; ++z;
+        }
+    }
+    uint64_t gamma() { uint32_t l = skip_zeros(); return (take(l) | (uint64_t(1) << l)) - 1; }       // integer_codes.hpp:21-25
+    uint64_t gamma_nonzero() { return gamma() + 1; }
+    uint64_t delta() { uint64_t l = gamma(); return (take(uint32_t(l)) | (uint64_t(1) << l)) - 1; }   // :41-45
+};
+
+// partitioned_sequence header at `offset` (partitioned_sequence.hpp:130-178) -> flat partitions
+static inline void pef_parse_sequence(bitvec_view const& bv, uint64_t offset, uint64_t universe, uint64_t n, global_params const& gp,
+                                      std::vector<PefPart>& out) {
+    bit_cursor it{bv, offset};
+    uint64_t partitions = it.gamma_nonzero();
+    if (partitions == 0 || partitions > n) throw format_error("bad partition count");
+    if (universe > 0x100000000ull) throw format_error("sequence universe beyond 32 bits");
+    if (partitions == 1) {
+        uint32_t universe_bits = uint32_t(ceil_log2_u64(universe));
+        uint64_t base = it.take(universe_bits);
+        uint64_t ub = 0;
+        if (n > 1) {
+            uint64_t universe_delta = it.delta();
+            ub = universe_delta ? universe_delta : (universe - base - 1);
+        }
+        out.push_back(PefPart{it.pos, 0u, uint32_t(n), uint32_t(base), uint32_t(base + ub)});
+        return;
+    }
+    uint64_t endpoint_bits = it.gamma();
+    uint64_t cur = it.pos;
+    std::vector<uint64_t> sizes = ef_decode_all(bv, cur, n, partitions - 1, gp);
+    cur += ef_offsets(0, n, partitions - 1, gp.ef_log_sampling0, gp.ef_log_sampling1).end;
+    std::vector<uint64_t> ubs = ef_decode_all(bv, cur, universe, partitions + 1, gp);
+    cur += ef_offsets(0, universe, partitions + 1, gp.ef_log_sampling0, gp.ef_log_sampling1).end;
+    uint64_t endpoints_offset = cur;
+    uint64_t sequences_offset = cur + endpoint_bits * (partitions - 1);
+    for (uint64_t p = 0; p < partitions; ++p) {
+        uint64_t endpoint = p ? get_bits(bv, endpoints_offset + (p - 1) * endpoint_bits, uint32_t(endpoint_bits)) : 0;
+        uint64_t begin = p ? sizes[p - 1] : 0, end = p + 1 < partitions ? sizes[p] : n;
+        if (end <= begin || end > n) throw format_error("partition sizes out of order");
+        uint64_t base = ubs[p] + (p ? 1 : 0), ub = ubs[p + 1];
+        if (ub < base || ub >= universe) throw format_error("partition bounds out of order");
+        out.push_back(PefPart{sequences_offset + endpoint, uint32_t(begin), uint32_t(end - begin), uint32_t(base), uint32_t(ub)});
+    }
+}
 
 struct PefIndexHost {
     uint64_t size = 0, num_docs = 0, device_bytes = 0;
-    std::vector<PefListDir> host_dir;
-    int load(const uint8_t*, size_t, std::string& err) { err = "opt index: not built yet"; return -4; }
+    struct host_list { uint64_t n; };
+    std::vector<host_list> host_dir;
+    PefSeqHost docs, freqs;
+    PefIndexDev dev{};
+
+    static int upload(PefSeqHost& s, bitvec_view const& bv, std::string& err) {
+        size_t words = size_t(bv.nwords) + 64;       // zero tail: scans read 32 words per step
+        if (cudaMalloc(reinterpret_cast<void**>(&s.d_bits), words * 8) != cudaSuccess) { err = "cudaMalloc failed (bit vector)"; return -3; }
+        cudaMemset(s.d_bits, 0, words * 8);
+        if (bv.nwords && cudaMemcpy(s.d_bits, bv.raw, size_t(bv.nwords) * 8, cudaMemcpyHostToDevice) != cudaSuccess) { err = "H2D copy failed"; return -3; }
+        if (cudaMalloc(reinterpret_cast<void**>(&s.d_lists), std::max<size_t>(1, s.lists.size()) * sizeof(PefListDir)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&s.d_parts), (s.parts.size() + 64) * sizeof(PefPart)) != cudaSuccess) { err = "cudaMalloc failed (directory)"; return -3; }
+        cudaMemset(s.d_parts, 0, (s.parts.size() + 64) * sizeof(PefPart));
+        cudaMemcpy(s.d_lists, s.lists.data(), s.lists.size() * sizeof(PefListDir), cudaMemcpyHostToDevice);
+        cudaMemcpy(s.d_parts, s.parts.data(), s.parts.size() * sizeof(PefPart), cudaMemcpyHostToDevice);
+        s.device_bytes = words * 8 + s.lists.size() * sizeof(PefListDir) + s.parts.size() * sizeof(PefPart);
+        return 0;
+    }
+
+    // freq_index::map (freq_index.hpp:234-243) + per-list headers (freq_index.hpp:192-214)
+    int load(const uint8_t* p, size_t nbytes, std::string& err) {
+        try {
+            byte_reader r(p, nbytes);
+            (void)r.get<uint64_t>();
+            global_params gp = read_params(r);
+            num_docs = r.get<uint64_t>();
+            if (num_docs == 0 || num_docs > 0xFFFFFFFFull) throw format_error("num_docs out of range");
+            uint64_t dsize = r.get<uint64_t>();
+            bitvec_view dend = read_bitvec(r), dbits = read_bitvec(r);
+            uint64_t fsize = r.get<uint64_t>();
+            bitvec_view fend = read_bitvec(r), fbits = read_bitvec(r);
+            if (dsize != fsize) throw format_error("docs and freqs collections differ in size");
+            size = dsize;
+            std::vector<uint64_t> dstart = ef_decode_all(dend, 0, dbits.bits, size, gp);
+            std::vector<uint64_t> fstart = ef_decode_all(fend, 0, fbits.bits, size, gp);
+            host_dir.resize(size);
+            docs.lists.resize(size); freqs.lists.resize(size);
+            for (uint64_t i = 0; i < size; ++i) {
+                bit_cursor it{dbits, dstart[i]};
+                uint64_t occurrences = it.gamma_nonzero();
+                uint64_t n = 1;
+                if (occurrences > 1) n = it.take(uint32_t(ceil_log2_u64(occurrences + 1)));
+                if (n == 0 || n > num_docs) throw format_error("bad list length");
+                host_dir[i].n = n;
+                docs.lists[i] = PefListDir{docs.parts.size(), 0u, uint32_t(n)};
+                pef_parse_sequence(dbits, it.pos, num_docs, n, gp, docs.parts);
+                docs.lists[i].nparts = uint32_t(docs.parts.size() - docs.lists[i].first_part);
+                freqs.lists[i] = PefListDir{freqs.parts.size(), 0u, uint32_t(n)};
+                pef_parse_sequence(fbits, fstart[i], occurrences + 1, n, gp, freqs.parts);
+                freqs.lists[i].nparts = uint32_t(freqs.parts.size() - freqs.lists[i].first_part);
+            }
+            int rc = upload(docs, dbits, err);
+            if (rc) return rc;
+            rc = upload(freqs, fbits, err);
+            if (rc) return rc;
+            auto mk = [&](PefSeqHost& s) {
+                PefSeq d;
+                d.bits = s.d_bits; d.lists = s.d_lists; d.parts = s.d_parts;
+                d.log_sampling0 = gp.ef_log_sampling0; d.log_sampling1 = gp.ef_log_sampling1;
+                d.rb_log_rank1_sampling = gp.rb_log_rank1_sampling; d.rb_log_sampling1 = gp.rb_log_sampling1;
+                return d;
+            };
+            dev.docs = mk(docs); dev.freqs = mk(freqs); dev.num_lists = size; dev.num_docs = uint32_t(num_docs);
+            device_bytes = docs.device_bytes + freqs.device_bytes;
+        } catch (std::exception const& e) {
+            err = e.what();
+            return -2;
+        }
+        return 0;
+    }
 };
 
-inline int pef_launch_query(PefIndexHost&, DevWand, DevBatch const&, int, uint32_t, int, int, std::string& err) { err = "opt index: not built yet"; return -4; }
-inline int pef_decode_lists(PefIndexHost&, const uint32_t*, uint32_t, const uint64_t*, uint32_t*, uint32_t*, int, std::string& err) { err = "opt index: not built yet"; return -4; }
-inline int pef_next_geq(PefIndexHost&, const uint32_t*, uint32_t, const uint64_t*, const uint64_t*, uint64_t*, uint64_t*, uint32_t*, int, std::string& err) { err = "opt index: not built yet"; return -4; }
+// ------------------------------------------------------------------------------------------------
+// host: launchers
+
+template <int OP>
+static int pef_launch_op(PefIndexHost& ix, DevWand wand, DevBatch const& db, uint32_t k, int max_terms, int sm_count, std::string& err) {
+    const int warps = 4;
+    size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes_t<PefState>(max_terms);
+    auto kern = pef_query_kernel<OP>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) { err = "cudaFuncSetAttribute failed"; return -3; }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+    if (per_sm < 1) { err = "opt query kernel does not fit on an SM"; return -3; }
+    int grid = std::max(1, std::min(per_sm * sm_count, int((db.nq + warps - 1) / warps)));
+    kern<<<grid, warps * 32, smem>>>(ix.dev, wand, db, k, max_terms);
+    return 0;
+}
+
+inline int pef_launch_query(PefIndexHost& ix, DevWand wand, DevBatch const& db, int op, uint32_t k, int max_terms, int sm_count, std::string& err) {
+    switch (op) {
+        case OP_AND: return pef_launch_op<OP_AND>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_AND_FREQ: return pef_launch_op<OP_AND_FREQ>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_OR: return pef_launch_op<OP_OR>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_OR_FREQ: return pef_launch_op<OP_OR_FREQ>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_RANKED_AND: return pef_launch_op<OP_RANKED_AND>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_WAND: return pef_launch_op<OP_WAND>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_MAXSCORE: return pef_launch_op<OP_MAXSCORE>(ix, wand, db, k, max_terms, sm_count, err);
+        case OP_RANKED_OR: return pef_launch_op<OP_RANKED_OR>(ix, wand, db, k, max_terms, sm_count, err);
+    }
+    err = "unknown operator";
+    return -1;
+}
+
+// d_terms / d_offsets are device arrays; partitions are counted on the host from the directory
+inline int pef_decode_lists(PefIndexHost& ix, const uint32_t* h_terms, const uint32_t* d_terms, uint32_t nterms, const uint64_t* d_offsets,
+                            uint32_t* d_docs, uint32_t* d_freqs, int sm_count, std::string& err) {
+    std::vector<uint64_t> prefix(size_t(nterms) + 1, 0);
+    for (uint32_t i = 0; i < nterms; ++i) prefix[i + 1] = prefix[i] + ix.docs.lists[h_terms[i]].nparts + ix.freqs.lists[h_terms[i]].nparts;
+    uint64_t* d_prefix = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&d_prefix), prefix.size() * 8) != cudaSuccess) { err = "cudaMalloc failed"; return -3; }
+    cudaMemcpy(d_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice);
+    PefDecodeJob job{d_terms, d_prefix, d_offsets, d_docs, d_freqs, prefix[nterms], nterms};
+    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((prefix[nterms] + 7) / 8, uint64_t(sm_count) * 8)));
+    pef_decode_kernel<<<grid, 256, 8 * 2048>>>(ix.dev, job);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_prefix);
+    if (e != cudaSuccess) { err = cudaGetErrorString(e); return -3; }
+    return 0;
+}
+
+inline int pef_next_geq(PefIndexHost& ix, const uint32_t* d_terms, uint32_t nlists, const uint64_t* d_bounds, const uint64_t* d_offsets,
+                        uint64_t* d_docids, uint64_t* d_freqs, uint32_t* d_counter, int sm_count, std::string&) {
+    PefGeqJob job{d_terms, d_bounds, d_offsets, d_docids, d_freqs, d_counter, nlists};
+    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(nlists) + 3) / 4, uint64_t(sm_count) * 8)));
+    pef_next_geq_kernel<<<grid, 128, 4 * sizeof(PefState)>>>(ix.dev, job);
+    return 0;
+}
 
 }  // namespace ds2i_gpu

@@ -81,22 +81,29 @@ __host__ __device__ constexpr size_t warp_smem_bytes(int slots) {
     return sizeof(WarpSmem) + size_t(slots) * sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4;
 }
 
-template <int CODEC, int OP>
-__global__ void __launch_bounds__(128) query_kernel(DevIndex idx, DevWand wand, DevBatch batch, uint32_t k, int slots) {
+template <typename State>
+__host__ __device__ constexpr size_t warp_smem_bytes_t(int slots) {
+    return sizeof(WarpSmem) + size_t(slots) * sizeof(State) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4;
+}
+
+// The reference's operators, literally: one warp per query, one candidate at a time, through an
+// enumerator E (BlockEnum for the block indexes, PefEnum for `opt`).
+template <class E, int OP>
+__device__ __forceinline__ void run_queries(typename E::Index const& idx, DevWand wand, DevBatch batch, uint32_t k, int slots, int codec) {
     s16_table_init(smem_words(0));
     __syncthreads();
 
-    typedef BlockEnum<CODEC> E;
+    typedef typename E::State State;
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes(slots);
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes_t<State>(slots);
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
-    ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
-    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState));
+    State* st = reinterpret_cast<State*>(base + sizeof(WarpSmem));
+    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(State));
     uint32_t* scratch = stage + STAGE_WORDS;
 
     WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar, idx.codec);
+    ctx_init(c, stage, scratch, &ws->bar, codec);
     const uint32_t N = idx.num_docs;
     constexpr bool RANKED = (OP == OP_RANKED_AND || OP == OP_WAND || OP == OP_MAXSCORE || OP == OP_RANKED_OR);
 
@@ -271,6 +278,11 @@ __global__ void __launch_bounds__(128) query_kernel(DevIndex idx, DevWand wand, 
         atomicAdd(&batch.stats[4], (unsigned long long)c.c_maxs);
         atomicAdd(&batch.stats[5], (unsigned long long)c.c_scored);
     }
+}
+
+template <int CODEC, int OP>
+__global__ void __launch_bounds__(128) query_kernel(DevIndex idx, DevWand wand, DevBatch batch, uint32_t k, int slots) {
+    run_queries<BlockEnum<CODEC>, OP>(idx, wand, batch, k, slots, idx.codec);
 }
 
 }  // namespace ds2i_gpu
