@@ -89,6 +89,18 @@ class Index:
                                                        _p(docs, C.c_uint32), _p(freqs, C.c_uint32), C.byref(ms)))
         return offs, docs[:total], freqs[:total], ms.value
 
+    def decode_lists_device(self, terms):
+        """Same decode, outputs left in HBM (no D2H): returns (postings, kernel_ms) — the batched block
+        decode microbenchmark (BASELINE config 2)."""
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        sizes = self.list_sizes(terms)
+        offs = np.zeros(len(terms) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(sizes, dtype=np.uint64)
+        ms = C.c_float()
+        _native.check(_native.lib().ds2i_gpu_decode_lists(self._h, _p(terms, C.c_uint32), len(terms), _p(offs, C.c_uint64),
+                                                       None, None, C.byref(ms)))
+        return int(offs[-1]), ms.value
+
     def next_geq_batch(self, terms, bounds_per_list):
         """index[term] opened, then next_geq(b) for each b (non-decreasing).  Returns (docids, freqs, ms)."""
         terms = np.ascontiguousarray(terms, dtype=np.uint32)

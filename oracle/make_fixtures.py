@@ -117,6 +117,18 @@ def main():
                         lens=np.array([len(docs[t]) for t in terms], dtype=np.uint64),
                         docs=np.concatenate([docs[t] for t in terms]), freqs=np.concatenate([freqs[t] for t in terms]),
                         sizes=np.asarray(sizes, dtype=np.uint32), source_terms=np.array(terms, dtype=np.uint32))
+    # ---- 1/10-scale synthetic collection (git-ignored): reference-built opt and block_optpfor indexes ----
+    builder = os.path.join(REPO, "ds2i_b200", "lib", "ds2i_build")
+    if os.access(builder, os.X_OK) and not os.path.exists(os.path.join(DATA, "S10.opt.idx")):
+        s10 = os.path.join(DATA, "S10")
+        run(builder, "gen", s10, "1000000", "100000", "20261017", "0.35", "2000")
+        for t in ("opt", "block_optpfor"):
+            run(os.path.join(BIN, "create_freq_index"), t, s10, s10 + "." + t + ".idx")
+        run(os.path.join(BIN, "create_wand_data"), s10, s10 + ".wand")
+        run(os.path.join(BIN, "ref_tool_strict"), "dump", "opt", s10 + ".opt.idx", s10 + ".wand", s10 + ".queries",
+            s10 + ".expected.strict.bin", "and:ranked_and:wand:maxscore", "10", "300")
+        for ext in (".docs", ".freqs", ".sizes"):
+            os.remove(s10 + ext)
     print("mini: %d lists, %d postings, %d queries" % (len(terms), sum(len(docs[t]) for t in terms), len(mq)))
     for f in sorted(os.listdir(GOLDEN)):
         print("  golden/%s %d bytes" % (f, os.path.getsize(os.path.join(GOLDEN, f))))
