@@ -588,34 +588,50 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, Decode
     WarpCtx c;
     ctx_init(c, stage, scratch, bar, idx.codec);
 
+    // a warp takes DECODE_CHUNK consecutive global block ids at a time: one binary search for the
+    // first list of the chunk, then the (list, block) cursor just walks forward
+    constexpr uint64_t DECODE_CHUNK = 32;
     const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
-    for (uint64_t g = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp; g < job.total_blocks; g += nwarps) {
-        // list containing global block g
+    const uint64_t nchunks = (job.total_blocks + DECODE_CHUNK - 1) / DECODE_CHUNK;
+    for (uint64_t ch = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp; ch < nchunks; ch += nwarps) {
+        const uint64_t g0 = ch * DECODE_CHUNK, g1 = min(job.total_blocks, g0 + DECODE_CHUNK);
         uint32_t lo = 0, hi = job.nterms;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
-            if (job.blk_prefix[mid] <= g) lo = mid; else hi = mid;
+            if (job.blk_prefix[mid] <= g0) lo = mid; else hi = mid;
         }
-        const uint32_t b = uint32_t(g - job.blk_prefix[lo]);
-        ListDir d = idx.dir[job.terms[lo]];
-        uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-        __syncwarp();
-        if (lane == 0) {
-            st->maxs_off = d.maxs_off;
-            st->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
-            st->n = d.n; st->nblocks = nblocks; st->data_bytes = d.data_bytes;
-        }
-        __syncwarp();
-        E::decode_docs_block(c, idx, st, b);
-        E::decode_freqs_block(c, idx, st);
-        const uint32_t size = st->cur_size;
-        const uint64_t o = job.out_offsets[lo] + uint64_t(b) * BLOCK;
+        uint32_t cur_list = 0xffffffffu;
+        uint64_t list_first = 0, list_end = 0, out_base = 0;
+        for (uint64_t g = g0; g < g1; ++g) {
+            while (cur_list == 0xffffffffu || g >= list_end) {
+                if (cur_list != 0xffffffffu) ++lo;
+                cur_list = lo;
+                list_first = job.blk_prefix[lo]; list_end = job.blk_prefix[lo + 1];
+                if (g < list_end) {
+                    ListDir d = idx.dir[job.terms[lo]];
+                    uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+                    __syncwarp();
+                    if (lane == 0) {
+                        st->maxs_off = d.maxs_off;
+                        st->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
+                        st->n = d.n; st->nblocks = nblocks; st->data_bytes = d.data_bytes;
+                    }
+                    __syncwarp();
+                    out_base = job.out_offsets[lo];
+                }
+            }
+            const uint32_t b = uint32_t(g - list_first);
+            E::decode_docs_block(c, idx, st, b);
+            E::decode_freqs_block(c, idx, st);
+            const uint32_t size = st->cur_size;
+            const uint64_t o = out_base + uint64_t(b) * BLOCK;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint32_t i = 32 * j + lane;
-            if (i < size) {
-                job.out_docs[o + i] = st->docs[i];
-                job.out_freqs[o + i] = st->freqs[i] + 1u;
+            for (uint32_t j = 0; j < 4; ++j) {
+                uint32_t i = 32 * j + lane;
+                if (i < size) {
+                    job.out_docs[o + i] = st->docs[i];
+                    job.out_freqs[o + i] = st->freqs[i] + 1u;
+                }
             }
         }
     }
@@ -649,7 +665,7 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
             rc = pef_decode_lists(*ix->pef, terms, d_terms.p, uint32_t(nterms), d_offs.p, d_docs.p, d_freqs.p, ix->sm_count, g_last_error);
         } else {
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
-            uint64_t want = (blk[nterms] + 7) / 8;
+            uint64_t want = (blk[nterms] / 32 + 8) / 8;
             int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
             decode_blocks_kernel<CODEC_ANY><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
         }
