@@ -358,4 +358,86 @@ __device__ __noinline__ uint32_t decode_interpolative_prefix(uint32_t win_off, u
     return __shfl_sync(FULL, consumed, 0);
 }
 
+// ---- Binary interpolative block, ONE LANE PER BLOCK --------------------------------------------
+// The code is bit-serial inside a block, but blocks are independent: in the batched decode each lane
+// of a warp takes its own block (list tails in every block index, every block of block_interpolative)
+// straight from global memory.  P (prefix sums) is written to `out` in tree order and converted in
+// place: docids = base + P[i] + i, freqs = P[i] - P[i-1] + 1.  Returns the bytes consumed.
+struct GlobalBitReader {
+    const uint32_t* word;   // next aligned word to load
+    uint64_t buf;
+    uint32_t avail;
+    uint32_t consumed_bits;
+    __device__ __forceinline__ void init(const uint8_t* p) {
+        uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        word = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+        uint32_t skip = uint32_t(a & 3u) * 8u;
+        buf = uint64_t(__ldg(word++)) >> skip;
+        avail = 32u - skip;
+        consumed_bits = 0;
+    }
+    __device__ __forceinline__ uint32_t read(uint32_t len) {
+        if (!len) return 0u;
+        if (avail < len) { buf |= uint64_t(__ldg(word++)) << avail; avail += 32u; }
+        uint32_t v = uint32_t(buf & ((uint64_t(1) << len) - 1));
+        buf >>= len; avail -= len; consumed_bits += len;
+        return v;
+    }
+};
+
+__device__ __forceinline__ uint32_t decode_interpolative_lane(const uint8_t* in, uint32_t n, uint32_t sum_of_values, uint32_t* out,
+                                                              bool as_docids, uint32_t docid_base) {
+    const uint8_t* p = in;
+    uint32_t sum = sum_of_values;
+    if (sum == 0xffffffffu) {                    // TightVariableByte prefix (block_codecs.hpp:131-134)
+        sum = 0;
+        for (uint32_t shift = 0; shift <= 28; shift += 7) {
+            uint32_t c = __ldg(p++);
+            sum += (c & 127u) << shift;
+            if (c & 128u) break;
+        }
+    }
+    out[n - 1] = sum;
+    uint32_t bits = 0;
+    if (n > 1) {
+        GlobalBitReader br;
+        br.init(p);
+        uint32_t stack[32];                      // pending right halves (base, cnt, low, high), depth <= 7
+        int sp = 0;
+        uint32_t base = 0, cnt = n - 1, low = 0, high = sum;
+        while (true) {
+            uint32_t h = cnt >> 1;
+            uint32_t u = high - low + 1u;
+            uint32_t val = 0;
+            if (u > 1u) {
+                uint32_t nb = 31u - __clz(u);
+                uint32_t m = (nb == 31u) ? (0u - u) : ((2u << nb) - u);
+                val = br.read(nb);
+                if (val >= m) val = (val << 1) + br.read(1) - m;
+            }
+            val += low;
+            out[base + h] = val;
+            uint32_t rc = cnt - h - 1u;
+            if (h) {
+                if (rc) { stack[4 * sp] = base + h + 1u; stack[4 * sp + 1] = rc; stack[4 * sp + 2] = val; stack[4 * sp + 3] = high; ++sp; }
+                cnt = h; high = val;
+            } else if (rc) {
+                base = base + 1u; cnt = rc; low = val;
+            } else {
+                if (!sp) break;
+                --sp;
+                base = stack[4 * sp]; cnt = stack[4 * sp + 1]; low = stack[4 * sp + 2]; high = stack[4 * sp + 3];
+            }
+        }
+        bits = br.consumed_bits;
+    }
+    if (as_docids) {
+        for (uint32_t i = 0; i < n; ++i) out[i] = docid_base + out[i] + i;
+    } else {
+        for (uint32_t i = n - 1; i > 0; --i) out[i] = out[i] - out[i - 1] + 1u;
+        out[0] += 1u;
+    }
+    return uint32_t(p - in) + ((bits + 7u) >> 3);
+}
+
 }  // namespace ds2i_gpu

@@ -621,6 +621,9 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, Decode
                 }
             }
             const uint32_t b = uint32_t(g - list_first);
+            // interpolative-coded blocks (list tails; every block of block_interpolative) are bit-serial:
+            // they are decoded one LANE per block by decode_serial_blocks_kernel instead
+            if (idx.codec == CODEC_INTERPOLATIVE || (uint64_t(b) + 1) * BLOCK > st->n) continue;
             E::decode_docs_block(c, idx, st, b);
             E::decode_freqs_block(c, idx, st);
             const uint32_t size = st->cur_size;
@@ -635,6 +638,32 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, Decode
             }
         }
     }
+}
+
+// one THREAD per interpolative-coded block, reading the bit stream straight from global memory
+__global__ void __launch_bounds__(128) decode_serial_blocks_kernel(DevIndex idx, DecodeJob job) {
+    const uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= job.total_blocks) return;
+    uint32_t lo = 0, hi = job.nterms;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job.blk_prefix[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t b = uint32_t(g - job.blk_prefix[lo]);
+    const ListDir d = idx.dir[job.terms[lo]];
+    const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+    const bool partial = (uint64_t(b) + 1) * BLOCK > d.n;
+    if (idx.codec != CODEC_INTERPOLATIVE && !partial) return;
+    const uint32_t size = partial ? d.n % BLOCK : BLOCK;
+    const uint8_t* maxs = idx.lists + d.maxs_off;
+    const uint8_t* ends = maxs + 4ull * nblocks;
+    const uint8_t* data = ends + 4ull * (nblocks - 1);
+    const uint32_t e0 = b ? ldg_u32_unaligned(ends + 4ull * (b - 1)) : 0u;
+    const uint32_t cur_base = (b ? ldg_u32_unaligned(maxs + 4ull * (b - 1)) : 0xffffffffu) + 1u;
+    const uint32_t cur_max = ldg_u32_unaligned(maxs + 4ull * b);
+    const uint64_t o = job.out_offsets[lo] + uint64_t(b) * BLOCK;
+    uint32_t used = decode_interpolative_lane(data + e0, size, cur_max - cur_base - (size - 1u), job.out_docs + o, true, cur_base);
+    decode_interpolative_lane(data + e0 + used, size, 0xffffffffu, job.out_freqs + o, false, 0u);
 }
 
 extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms,
@@ -667,7 +696,9 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
             uint64_t want = (blk[nterms] / 32 + 8) / 8;
             int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
-            decode_blocks_kernel<CODEC_ANY><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
+            if (ix->codec != CODEC_INTERPOLATIVE)
+                decode_blocks_kernel<CODEC_ANY><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
+            decode_serial_blocks_kernel<<<unsigned((blk[nterms] + 127) / 128), 128>>>(ix->dev, job);
         }
     }
     CUDA_TRY(cudaEventRecord(e1));
