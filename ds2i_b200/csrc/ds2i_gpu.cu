@@ -42,20 +42,31 @@ static int fail(int code, std::string const& msg) { g_last_error = msg; return c
             return fail(DS2I_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
+// Device buffers come from the stream-ordered allocator with a pool that never trims: after the
+// first batch a query_batch call allocates and frees without touching the driver's slow paths
+// (cudaFree used to cost up to 290 ms per call in the end-to-end path).
+static void tune_mem_pool(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = ~uint64_t(0);
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+}
+
 template <typename T>
 struct dev_buf {
     T* p = nullptr;
     size_t n = 0;
-    ~dev_buf() { if (p) cudaFree(p); }
+    ~dev_buf() { if (p) cudaFreeAsync(p, 0); }
     cudaError_t alloc(size_t count) {
-        if (p) { cudaFree(p); p = nullptr; }
+        if (p) { cudaFreeAsync(p, 0); p = nullptr; }
         n = count;
-        return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+        return cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T), 0);
     }
     cudaError_t upload(std::vector<T> const& v) {
         cudaError_t e = alloc(v.size());
         if (e != cudaSuccess || v.empty()) return e;
-        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, 0);
     }
 };
 
@@ -158,6 +169,7 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
     std::unique_ptr<ds2i_gpu_index> ix(new ds2i_gpu_index);
     ix->device = device; ix->kind = kind; ix->codec = codec;
     cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device);
+    tune_mem_pool(device);
     try {
         const uint8_t* p = static_cast<const uint8_t*>(file_bytes);
         if (kind == KIND_PEF) {
