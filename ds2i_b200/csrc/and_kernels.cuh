@@ -24,6 +24,7 @@ struct AndJob {
     const AndItem* items;      // in query order (item_begin[q] .. item_begin[q+1])
     const uint32_t* order;     // processing order: items of the costliest queries first
     uint32_t nitems;
+    uint32_t chunk_blocks;     // blocks of the shortest list per item (<= 32)
     uint32_t* work_counter;
     uint32_t* item_counts;     // nitems: matches found by the item
     uint32_t* item_sizes;      // nitems: entries in the item's partial top-k
@@ -37,7 +38,7 @@ struct AndJob {
 // 32-ary search and a separate metadata fetch.
 struct BlockMeta { uint32_t block, e0, e1, prev_max, cur_max; bool have; };
 
-__device__ __forceinline__ BlockMeta find_block(WarpCtx& c, const ListState* s, const uint8_t* maxs, uint32_t lo, uint32_t lo_prev_max, uint32_t bound) {
+__device__ DS2I_DECODE_INLINE BlockMeta find_block(WarpCtx& c, const ListState* s, const uint8_t* maxs, uint32_t lo, uint32_t lo_prev_max, uint32_t bound) {
     const unsigned lane = lane_id();
     const uint32_t nblocks = s->nblocks;
     const uint8_t* ends = maxs + 4ull * nblocks;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wa
         __syncwarp();
 
         const uint32_t nb0 = st[0].nblocks;
-        const uint32_t b_end = min(nb0, item.first_block + AND_CHUNK_BLOCKS);
+        const uint32_t b_end = min(nb0, item.first_block + job.chunk_blocks);
         // metadata of the whole chunk of the driving list, one block per lane, fetched in one round trip
         uint32_t m_max = 0, m_start = 0, m_end = 0, m_first_prev;
         {

@@ -117,6 +117,13 @@ __device__ __forceinline__ uint32_t decode_values(WarpCtx& c, uint32_t off, uint
     return decode_interpolative_prefix(smem_offset(c.stage), off, size, sum_of_values, smem_offset(buf), smem_offset(c.scratch));
 }
 
+// Inlining policy of the block decoder wrappers.  Measured on B200 (round 1): __noinline__ here shrinks the
+// kernels but costs more in spilled WarpCtx state than it saves in instruction-cache misses
+// (ranked_and 26 -> 30 ms, wand 160 -> 183 ms per 10k-query batch), so they stay inlined.
+#ifndef DS2I_DECODE_INLINE
+#define DS2I_DECODE_INLINE __forceinline__
+#endif
+
 template <int CODEC>
 struct BlockEnum {
     typedef ListState State;
@@ -159,7 +166,7 @@ struct BlockEnum {
 
     // the same with the block's metadata already in hand: e0/e1 = byte range of the block inside the
     // list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
-    static __device__ __forceinline__ void decode_docs_block_meta(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b,
+    static __device__ DS2I_DECODE_INLINE void decode_docs_block_meta(WarpCtx& c, DevIndex const& idx, ListState* st, uint32_t b,
                                                                   uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
         const unsigned lane = lane_id();
         const uint32_t n = st->n;

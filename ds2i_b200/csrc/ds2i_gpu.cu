@@ -127,7 +127,7 @@ struct ds2i_gpu_batch {
     dev_buf<AndItem> and_items;
     dev_buf<uint32_t> and_order, and_item_begin, and_item_counts, and_item_sizes;
     dev_buf<float> and_item_scores;
-    uint32_t n_and_items = 0, n_and_items_large = 0;
+    uint32_t n_and_items = 0, n_and_items_large = 0, and_chunk = AND_CHUNK_BLOCKS;
     // block-parallel union path (wand / maxscore): work items = (query, docid range)
     dev_buf<UnionItem> un_items;
     dev_buf<uint32_t> un_order, un_item_begin, un_item_sizes, un_threshold;
@@ -329,12 +329,15 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     std::iota(sched.begin(), sched.end(), 0u);
     std::stable_sort(sched.begin(), sched.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
 
-    // work items of the conjunctive path
+    // work items of the conjunctive path (DS2I_GPU_AND_CHUNK_BLOCKS: blocks of the shortest list per item, <= 32)
+    uint32_t and_chunk = AND_CHUNK_BLOCKS;
+    if (const char* ev = getenv("DS2I_GPU_AND_CHUNK_BLOCKS")) and_chunk = std::min<uint32_t>(32, std::max<uint32_t>(1, uint32_t(atoi(ev))));
+    b->and_chunk = and_chunk;
     std::vector<AndItem> items;
     std::vector<uint32_t> item_begin(nq + 1, 0), item_order;
     for (size_t q = 0; q < nq; ++q) {
         uint64_t nb0 = (shortest[q] + BLOCK - 1) / BLOCK;
-        for (uint64_t fb = 0; fb < nb0; fb += AND_CHUNK_BLOCKS) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
+        for (uint64_t fb = 0; fb < nb0; fb += and_chunk) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
         item_begin[q + 1] = uint32_t(items.size());
     }
     // two occupancy classes: queries with few terms run with small per-warp shared memory (more
@@ -359,7 +362,7 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
         std::vector<uint32_t> ubegin(nq + 1, 0), uorder;
         // postings per work item; DS2I_GPU_UNION_ITEM_POSTINGS overrides it (tests use a tiny value to
         // exercise the range-splitting path on small collections)
-        uint64_t per_item = 32768;
+        uint64_t per_item = 131072;
         if (const char* ev = getenv("DS2I_GPU_UNION_ITEM_POSTINGS")) per_item = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
         for (size_t q = 0; q < nq; ++q) {
             if (q_begin[q + 1] > q_begin[q]) {
@@ -430,7 +433,7 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
         int grid = per_sm * ix->sm_count;
         int needed = int((count + warps - 1) / warps);
         if (grid > needed) grid = std::max(needed, 1);
-        AndJob job{b->and_items.p, b->and_order.p + first, count, b->work_counter.p + 1 + cls, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
+        AndJob job{b->and_items.p, b->and_order.p + first, count, b->and_chunk, b->work_counter.p + 1 + cls, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
         kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, slots);
         b->launches += 1;
     }

@@ -55,7 +55,7 @@ struct UnionOps {
     typedef BlockEnum<CODEC> E;
 
     // freqs of the list's current block as plain values (freq - 1) in dst[0..size)
-    static __device__ __forceinline__ void decode_freqs_plain(WarpCtx& c, DevIndex const& idx, ListState* s, uint32_t* dst) {
+    static __device__ DS2I_DECODE_INLINE void decode_freqs_plain(WarpCtx& c, DevIndex const& idx, ListState* s, uint32_t* dst) {
         const unsigned lane = lane_id();
         uint32_t off = stage_range(c, idx.lists, s->data_off + s->freqs_off, s->data_off + s->block_end);
         bool prefix;
