@@ -133,6 +133,7 @@ struct ds2i_gpu_batch {
     dev_buf<uint32_t> un_order, un_item_begin, un_item_sizes, un_threshold;
     dev_buf<float> un_item_scores;
     uint32_t n_un_items = 0;
+    unsigned items_built = 3;      // which work-item lists exist (bit 0 conjunctive, bit 1 union)
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~ds2i_gpu_batch() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
@@ -278,14 +279,23 @@ static float query_term_weight(uint64_t freq, uint64_t df, uint64_t num_docs) {
     return f * std::max(epsilon_score, idf) * (1.0f + 1.2f);
 }
 
+// which: bit 0 = build the work items of the conjunctive path, bit 1 = of the union path
+static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uint32_t* terms,
+                              const uint64_t* query_offsets, size_t nq, unsigned which, ds2i_gpu_batch** out);
+
 extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uint32_t* terms,
                                       const uint64_t* query_offsets, size_t nq, ds2i_gpu_batch** out) {
+    return batch_prepare_impl(ix, wand, terms, query_offsets, nq, 3u, out);
+}
+
+static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uint32_t* terms,
+                              const uint64_t* query_offsets, size_t nq, unsigned which, ds2i_gpu_batch** out) {
     if (!ix || !out || !query_offsets || (!terms && nq && query_offsets[nq])) return fail(DS2I_E_ARG, "null argument");
     if (nq > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many queries in one batch");
     if (wand && wand->num_docs < ix->num_docs) return fail(DS2I_E_ARG, "wand data has fewer documents than the index");
     CUDA_TRY(cudaSetDevice(ix->device));
     std::unique_ptr<ds2i_gpu_batch> b(new ds2i_gpu_batch);
-    b->index = ix; b->wand = wand; b->nq = uint32_t(nq);
+    b->index = ix; b->wand = wand; b->nq = uint32_t(nq); b->items_built = which;
 
     std::vector<uint32_t> q_begin(nq + 1, 0), term, sched(nq);
     std::vector<float> q_weight, max_weight;
@@ -335,7 +345,7 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     b->and_chunk = and_chunk;
     std::vector<AndItem> items;
     std::vector<uint32_t> item_begin(nq + 1, 0), item_order;
-    for (size_t q = 0; q < nq; ++q) {
+    for (size_t q = 0; q < nq && (which & 1u); ++q) {
         uint64_t nb0 = (shortest[q] + BLOCK - 1) / BLOCK;
         for (uint64_t fb = 0; fb < nb0; fb += and_chunk) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
         item_begin[q + 1] = uint32_t(items.size());
@@ -365,7 +375,7 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
         uint64_t per_item = 131072;
         if (const char* ev = getenv("DS2I_GPU_UNION_ITEM_POSTINGS")) per_item = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
         for (size_t q = 0; q < nq; ++q) {
-            if (q_begin[q + 1] > q_begin[q]) {
+            if ((which & 2u) && q_begin[q + 1] > q_begin[q]) {
                 uint64_t r = std::min<uint64_t>(64, std::max<uint64_t>(1, (cost[q] + per_item - 1) / per_item));
                 for (uint64_t i = 0; i < r; ++i) {
                     uint64_t lo = ix->num_docs * i / r, hi = ix->num_docs * (i + 1) / r;
@@ -501,11 +511,11 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     int rc = DS2I_OK;
     if (b->nq) {
         if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
-        else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND)) {
+        else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
             if (!ranked) k = 1;
             rc = op == OP_AND ? launch_and_block<CODEC_ANY, false>(b, db, k) : launch_and_block<CODEC_ANY, true>(b, db, k);
         }
-        else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE)) {
+        else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u)) {
             rc = launch_union_block<CODEC_ANY>(b, db, k);
         }
         else rc = launch_query_op<CODEC_ANY>(b, db, op, k);
@@ -561,7 +571,8 @@ extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int
     static const bool trace = getenv("DS2I_GPU_TRACE") != nullptr;
     double t0 = now_ms();
     ds2i_gpu_batch* b = nullptr;
-    int rc = ds2i_gpu_batch_prepare(ix, wand, terms, query_offsets, nq, &b);
+    unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE) ? 2u : 0u;
+    int rc = batch_prepare_impl(ix, wand, terms, query_offsets, nq, which, &b);
     if (rc != DS2I_OK) return rc;
     std::unique_ptr<ds2i_gpu_batch> guard(b);
     double t1 = now_ms();
