@@ -457,7 +457,7 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
     auto kern = union_block_kernel<CODEC>;
-    size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(b->max_terms + 1);
+    size_t smem = S16_TAB_BYTES + warps * union_warp_smem_bytes(b->max_terms);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));

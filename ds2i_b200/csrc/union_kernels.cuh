@@ -92,6 +92,9 @@ struct UnionOps {
     }
 };
 
+constexpr size_t UNION_MERGE_BYTES = 128 * 4 + 128 * 4 + 128 * 2;
+__host__ __device__ constexpr size_t union_warp_smem_bytes(int slots) { return warp_smem_bytes(slots) + UNION_MERGE_BYTES; }
+
 template <int CODEC>
 __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, UnionJob job, uint32_t k, int slots) {
     s16_table_init(smem_words(0));
@@ -101,12 +104,14 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
     typedef UnionOps<CODEC> U;
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    // one extra ListState-sized slot at the end serves as the freqs scratch of probed lists
-    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes(slots + 1);
+    // per warp: [WarpSmem | slots x ListState | merge buffers | staging window | codec scratch]
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * union_warp_smem_bytes(slots);
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
     ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
-    uint32_t* ftmp = st[slots].docs;
-    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots + 1) * sizeof(ListState));
+    uint32_t* cdoc = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState));   // merged candidate docids
+    uint32_t* ftmp = cdoc + 128;                                                                              // freqs of a probed block
+    uint16_t* cinfo = reinterpret_cast<uint16_t*>(ftmp + 128);                                                // (list << 8) | slot per candidate
+    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState) + UNION_MERGE_BYTES);
     uint32_t* scratch = stage + STAGE_WORDS;
 
     WarpCtx c;
@@ -187,7 +192,8 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                 }
             }
 
-            // window: everything up to the smallest current block_max of the live essential lists
+            // window: everything up to the smallest current block_max of the live essential lists, shrunk until
+            // the essential postings inside it number at most 128 (one merged candidate batch per window)
             uint32_t w_hi = 0xffffffffu;
             bool any = false;
             for (uint32_t e = ne; e < nt; ++e) {
@@ -198,60 +204,85 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
             }
             if (!any) break;
             if (w_hi >= hi) w_hi = hi - 1;
-            for (uint32_t i = 0; i < ne; ++i) if (lane == 0) st[i].win_block = st[i].cur_block;
-            __syncwarp();
+            uint32_t total;
+            while (true) {
+                total = 0;
+                uint32_t best_cnt = 0, best_e = ne;
+                for (uint32_t e = ne; e < nt; ++e) {
+                    ListState* s = &st[e];
+                    uint32_t end_e = s->exhausted ? s->pos : U::count_less(s, w_hi + 1u);     // elements <= w_hi
+                    uint32_t cnt = end_e > s->pos ? end_e - s->pos : 0u;
+                    if (lane == 0) s->pad = s->pos + cnt;                                        // window end inside the block
+                    if (cnt > best_cnt) { best_cnt = cnt; best_e = e; }
+                    total += cnt;
+                }
+                __syncwarp();
+                if (total <= 128u) break;
+                uint32_t take = max(1u, best_cnt * 120u / total);
+                w_hi = st[best_e].docs[st[best_e].pos + take - 1u];
+            }
 
-            for (uint32_t e = ne; e < nt; ++e) {
-                ListState* se = &st[e];
-                if (se->exhausted) continue;
-                const uint32_t pos_e = se->pos;
-                const uint32_t end_e = U::count_less(se, w_hi + 1u);       // elements <= w_hi
-                if (end_e <= pos_e) continue;
-                // candidates of this group: positions [pos_e, end_e) of list e's block
-                uint32_t cand[4], alive = 0;
-                float score[4], nl[4];
-                {
+            if (total) {
+                // merged, sorted candidate batch: rank of a posting = postings of the window that precede it
+                // (ties between lists broken by list order, so copies of one document sit next to each other
+                // in increasing max_weight order — the reference's summation order, queries.hpp:545-554)
+                for (uint32_t e = ne; e < nt; ++e) {
+                    const ListState* se = &st[e];
+                    const uint32_t pos_e = se->pos, end_e = se->pad;
+                    if (end_e <= pos_e) continue;
                     uint4 cv = reinterpret_cast<const uint4*>(se->docs)[lane];
-                    cand[0] = cv.x; cand[1] = cv.y; cand[2] = cv.z; cand[3] = cv.w;
-                }
+                    const uint32_t x[4] = {cv.x, cv.y, cv.z, cv.w};
+                    uint32_t rank[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t slot = 4 * lane + j;
-                    if (slot >= pos_e && slot < end_e) alive |= 1u << j;
-                    score[j] = 0.f; nl[j] = 0.f;
-                }
-                // essential part, lists in increasing max_weight order; a document belongs to the first
-                // essential list that contains it
-                for (uint32_t e2 = ne; e2 < nt; ++e2) {
-                    if (e2 == e) {
+                    for (int j = 0; j < 4; ++j) rank[j] = 4 * lane + j - pos_e;
+                    for (uint32_t e2 = ne; e2 < nt; ++e2) {
+                        if (e2 == e) continue;
+                        const ListState* s2 = &st[e2];
+                        const uint32_t pos2 = s2->pos, end2 = s2->pad;
+                        if (end2 <= pos2) continue;
+                        const uint32_t* d2 = s2->docs;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (alive & (1u << j)) {
-                                if (e2 == ne || nl[j] == 0.f) nl[j] = __ldg(wand.norm_lens + cand[j]);
-                                score[j] += ws->qw[e] * doc_term_weight(se->freqs[4 * lane + j] + 1u, nl[j]);
-                            }
-                        continue;
-                    }
-                    const ListState* s2 = &st[e2];
-                    if (s2->exhausted) continue;
-                    const uint32_t* d2 = s2->docs;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (alive & (1u << j)) {
-                            uint32_t p = lower_bound128(d2, cand[j]);
-                            if (d2[p] == cand[j]) {
-                                if (e2 < e) alive &= ~(1u << j);       // already scored from list e2's group
-                                else {
-                                    if (nl[j] == 0.f) nl[j] = __ldg(wand.norm_lens + cand[j]);
-                                    score[j] += ws->qw[e2] * doc_term_weight(s2->freqs[p] + 1u, nl[j]);
-                                }
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t slot = 4 * lane + j;
+                            if (slot >= pos_e && slot < end_e) {
+                                uint32_t lb = lower_bound128(d2, x[j]);
+                                rank[j] += lb - pos2;
+                                if (e2 < e && lb < end2 && d2[lb] == x[j]) rank[j] += 1u;
                             }
                         }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t slot = 4 * lane + j;
+                        if (slot >= pos_e && slot < end_e) { cdoc[rank[j] & 127u] = x[j]; cinfo[rank[j] & 127u] = uint16_t((e << 8) | slot); }
+                    }
                 }
-                unsigned n_owned = __reduce_add_sync(FULL, __popc(alive));
-                c.c_scored += n_owned;
+                __syncwarp();
 
-                // non-essential lists from the highest bound down (queries.hpp:557-566)
+                // every lane owns 4 consecutive entries of the merged batch; an entry that repeats its
+                // predecessor's docid is a copy and is folded into the first one
+                uint32_t cand[4], alive = 0;
+                float score[4], nl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r = 4 * lane + j;
+                    cand[j] = r < total ? cdoc[r] : 0xffffffffu;
+                    score[j] = 0.f; nl[j] = 0.f;
+                    if (r < total && (r == 0 || cdoc[r - 1] != cand[j])) {
+                        alive |= 1u << j;
+                        nl[j] = __ldg(wand.norm_lens + cand[j]);
+                        for (uint32_t t = 0; t < nt - ne; ++t) {
+                            uint32_t r2 = r + t;
+                            if (r2 >= total || cdoc[r2] != cand[j]) break;
+                            uint32_t info = cinfo[r2];
+                            score[j] += ws->qw[info >> 8] * doc_term_weight(st[info >> 8].freqs[info & 127u] + 1u, nl[j]);
+                        }
+                    }
+                }
+                c.c_scored += __reduce_add_sync(FULL, __popc(alive));
+
+                // non-essential lists from the highest bound down (queries.hpp:557-566); candidates are sorted,
+                // so every list is probed in one forward pass
                 uint32_t probing = alive;
                 for (uint32_t i = ne; i-- > 0;) {
 #pragma unroll
@@ -262,7 +293,6 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                     if (s->exhausted) continue;
                     const uint8_t* maxs = idx.lists + s->maxs_off;
                     uint32_t pending = probing;
-                    bool first_lookup = true;
                     while (true) {
                         uint32_t mine = 0xffffffffu;
 #pragma unroll
@@ -271,18 +301,6 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                         if (cmin == 0xffffffffu) break;
                         if (cmin > s->last_max) break;                 // nothing of list i at or beyond cmin
                         uint32_t cur_block = s->cur_block;
-                        if (first_lookup && cur_block != 0xffffffffu && s->prev_max != 0xffffffffu && cmin <= s->prev_max) {
-                            // an earlier group of this window moved the cursor past cmin: step back to where the window began
-                            uint32_t wb = s->win_block;
-                            if (wb == 0xffffffffu) {
-                                if (lane == 0) { s->cur_block = 0xffffffffu; s->cur_max = 0; s->prev_max = 0xffffffffu; }
-                                __syncwarp();
-                            } else {
-                                E::decode_docs_block(c, idx, s, wb);
-                            }
-                            cur_block = s->cur_block;
-                        }
-                        first_lookup = false;
                         if (cur_block == 0xffffffffu || cmin > s->cur_max) {
                             bool fresh = cur_block == 0xffffffffu;
                             BlockMeta bm = find_block(c, s, maxs, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max, cmin);
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                     }
                 }
                 __syncwarp();
-                if (lane == 0) se->pos = end_e;
+                if (lane >= ne && lane < nt) st[lane].pos = st[lane].pad;       // cursors move past the window
                 __syncwarp();
             }
 
