@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--ref-sample", type=int, default=2000, help="queries per step of the CPU reference runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary wand measurement of the default run")
     ap.add_argument("--check", type=int, default=200, help="queries checked against the reference in the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
@@ -214,53 +215,65 @@ def main():
     log("[bench] rank %d: index in HBM (%.1f MB) + %d queries in %.1f s" % (rank, index.device_bytes() / 1e6, len(queries), time.time() - t0))
     batch = d.QueryBatch(index, wdata, queries)
 
-    def step():
-        ms = batch.run(args.op, args.k)
-        if world > 1:
-            counts_t, scores_t = batch.device_results(args.k)
-            gather_topk(counts_t, scores_t, world)
-        return ms
-
-    for _ in range(args.warmup):
-        step()
-    launches0 = batch.stats()["launches"]
-    kernel_ms = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            kernel_ms.append(step())
-        ev1.record()
-        barrier()
-    total_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    stats = batch.stats()
-    counts, scores = batch.fetch()
-
-    # end to end through the public call with host buffers (H2D + D2H + host-side preparation inside)
-    e2e_steps = max(2, min(args.steps, 3))
     host_buffers = d.flatten_queries(queries)          # the caller's host buffers (terms, offsets)
-    d.query_batch(index, wdata, args.op, host_buffers, args.k)
-    barrier()
-    te = time.perf_counter()
-    for _ in range(e2e_steps):
-        c2, s2, _ = d.query_batch(index, wdata, args.op, host_buffers, args.k)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - te) / e2e_steps
-    te_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(te_t.item())
-    # same results through both entry points (the union kernel's last score bit depends on the pruning history)
-    assert np.array_equal(c2, counts)
-    assert np.all(np.abs(s2.astype(np.float64) - scores) <= 1e-5 * np.maximum(np.abs(scores), 1e-30))
     nterms = sum(len(q) for q in queries)
     h2d = nterms * 4 + (len(queries) + 1) * 8
     d2h = len(queries) * 8 + len(queries) * args.k * 4
+
+    def measure(op):
+        """W warm-up + K timed steps of `op` over the resident batch, then the end-to-end leg."""
+        def step():
+            ms = batch.run(op, args.k)
+            if world > 1:
+                counts_t, scores_t = batch.device_results(args.k)
+                gather_topk(counts_t, scores_t, world)
+            return ms
+
+        for _ in range(args.warmup):
+            step()
+        launches0 = batch.stats()["launches"]
+        kernel_ms = []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                kernel_ms.append(step())
+            ev1.record()
+            barrier()
+        total_ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        stats = batch.stats()
+        counts, scores = batch.fetch()
+
+        # end to end through the public call with host buffers (H2D + D2H + host-side preparation inside)
+        e2e_steps = max(2, min(args.steps, 3))
+        d.query_batch(index, wdata, op, host_buffers, args.k)
+        barrier()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            c2, s2, _ = d.query_batch(index, wdata, op, host_buffers, args.k)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - te) / e2e_steps
+        te_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        e2e_s = float(te_t.item())
+        # same results through both entry points (the union kernel's last score bit depends on the pruning history)
+        assert np.array_equal(c2, counts)
+        assert np.all(np.abs(s2.astype(np.float64) - scores) <= 1e-5 * np.maximum(np.abs(scores), 1e-30))
+        return {"total_ms": total_ms, "kernel_ms": kernel_ms, "stats": stats, "launches": stats["launches"] - launches0,
+                "counts": counts, "scores": scores, "clocks": clocks.summary(), "e2e_s": e2e_s}
+
+    m = measure(args.op)
+    also = {}
+    if args.op == "ranked_and" and not args.no_also:
+        also["wand"] = measure("wand")            # the second half of BASELINE.json's metric, same protocol
+    total_ms, kernel_ms, stats, counts, scores, clocks_summary, e2e_s = (m["total_ms"], m["kernel_ms"], m["stats"], m["counts"],
+                                                                          m["scores"], m["clocks"], m["e2e_s"])
 
     if rank != 0:
         if world > 1:
@@ -286,13 +299,19 @@ def main():
                    "seed": args.seed, "index_bytes": index.device_bytes(),
                    "l2": "no flush: index (%.0f MB) and per-step touched bytes exceed the 126 MB L2" % (index.device_bytes() / 1e6),
                    "parallelism": "query batch sharded over %d GPU(s), index replicated, NCCL all_gather of top-k" % world},
-        "clocks": clocks.summary(),
+        "clocks": clocks_summary,
         "e2e": {"value": nq_total / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": stats["launches"] - launches0,
+        "gpu_launches": m["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch(args.op),
                      "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
                      "counters": stats},
     }
+
+    for op2, m2 in also.items():
+        ms2 = m2["total_ms"] / args.steps
+        line.setdefault("also", {})[op2] = {"metric": METRIC % op2, "value": nq_total / (ms2 * 1e-3), "unit": "queries/s", "ms_per_step": ms2,
+                                            "e2e": {"value": nq_total / m2["e2e_s"], "unit": "queries/s"}, "gpu_launches": m2["launches"],
+                                            "counters": m2["stats"]}
 
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -301,6 +320,10 @@ def main():
             out = run_reference_tool(paths, args.op, cores, sample, 2)
             line["cpu_baseline"] = {"value": sample / out["pass_seconds"][-1], "unit": "queries/s", "cores": cores, "kind": "reference",
                                     "sample": "first %d queries, second of 2 passes, ds2i %s_query compiled from the reference sources, all host threads" % (sample, args.op)}
+            for op2 in also:
+                out2 = run_reference_tool(paths, op2, cores, sample, 2)
+                line["also"][op2]["cpu_baseline"] = {"value": sample / out2["pass_seconds"][-1], "unit": "queries/s", "cores": cores, "kind": "reference",
+                                                     "sample": "first %d queries, second of 2 passes, all host threads" % sample}
             # parity at full size: the reference's own results for the first queries (the checker, not the product)
             ncheck = min(args.check, len(queries))
             if ncheck:

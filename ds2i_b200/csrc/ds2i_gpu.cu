@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <ctime>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -279,6 +280,27 @@ static float query_term_weight(uint64_t freq, uint64_t df, uint64_t num_docs) {
     return f * std::max(epsilon_score, idf) * (1.0f + 1.2f);
 }
 
+static double now_ms() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static bool trace_on() { static const bool t = getenv("DS2I_GPU_TRACE") != nullptr; return t; }
+
+// cudaFuncSetAttribute + the occupancy query are not free: do them once per (kernel, shared-memory size)
+static int cached_blocks_per_sm(const void* kern, int threads, size_t smem, int* out) {
+    struct key { const void* k; size_t s; int v; };
+    static std::vector<key> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto const& c : cache) if (c.k == kern && c.s == smem) { *out = c.v; return DS2I_OK; }
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    cache.push_back(key{kern, smem, per_sm});
+    *out = per_sm;
+    return DS2I_OK;
+}
+
 // which: bit 0 = build the work items of the conjunctive path, bit 1 = of the union path
 static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uint32_t* terms,
                               const uint64_t* query_offsets, size_t nq, unsigned which, ds2i_gpu_batch** out);
@@ -296,6 +318,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     CUDA_TRY(cudaSetDevice(ix->device));
     std::unique_ptr<ds2i_gpu_batch> b(new ds2i_gpu_batch);
     b->index = ix; b->wand = wand; b->nq = uint32_t(nq); b->items_built = which;
+    const double tp0 = now_ms();
 
     std::vector<uint32_t> q_begin(nq + 1, 0), term, sched(nq);
     std::vector<float> q_weight, max_weight;
@@ -339,6 +362,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     std::iota(sched.begin(), sched.end(), 0u);
     std::stable_sort(sched.begin(), sched.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
 
+    const double tp1 = now_ms();
     // work items of the conjunctive path (DS2I_GPU_AND_CHUNK_BLOCKS: blocks of the shortest list per item, <= 32)
     uint32_t and_chunk = AND_CHUNK_BLOCKS;
     if (const char* ev = getenv("DS2I_GPU_AND_CHUNK_BLOCKS")) and_chunk = std::min<uint32_t>(32, std::max<uint32_t>(1, uint32_t(atoi(ev))));
@@ -392,6 +416,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         CUDA_TRY(b->un_threshold.alloc(nq));
     }
 
+    const double tp2 = now_ms();
     b->max_terms = max_terms;
     CUDA_TRY(b->q_begin.upload(q_begin)); CUDA_TRY(b->term.upload(term)); CUDA_TRY(b->sched.upload(sched));
     CUDA_TRY(b->q_weight.upload(q_weight)); CUDA_TRY(b->max_weight.upload(max_weight));
@@ -401,6 +426,8 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     CUDA_TRY(b->stats.alloc(8));
     CUDA_TRY(cudaMemset(b->stats.p, 0, 8 * sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreate(&b->ev0)); CUDA_TRY(cudaEventCreate(&b->ev1));
+    if (trace_on()) fprintf(stderr, "[ds2i_gpu] prepare: per-query host work %.2f ms, work items + their uploads %.2f ms, remaining uploads %.2f ms\n",
+                            tp1 - tp0, tp2 - tp1, now_ms() - tp2);
     *out = b.release();
     return DS2I_OK;
 }
@@ -411,9 +438,9 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     const int warps = 4;
     size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(b->max_terms);
     auto kern = query_kernel<CODEC, OP>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
+    if (orc != DS2I_OK) return orc;
     if (per_sm < 1) return fail(DS2I_E_CUDA, "query kernel does not fit on an SM");
     int grid = per_sm * ix->sm_count;
     int needed = int((b->nq + warps - 1) / warps);
@@ -436,9 +463,9 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
         if (!count) continue;
         int slots = cls == 0 ? b->max_terms : std::min(b->max_terms, AND_SMALL_TERMS);
         size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(slots);
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S16_TAB_BYTES + warps * warp_smem_bytes(MAX_TERMS))));
         int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+        int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
+        if (orc != DS2I_OK) return orc;
         if (per_sm < 1) return fail(DS2I_E_CUDA, "conjunctive kernel does not fit on an SM");
         int grid = per_sm * ix->sm_count;
         int needed = int((count + warps - 1) / warps);
@@ -458,9 +485,9 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
     const int warps = 4;
     auto kern = union_block_kernel<CODEC>;
     size_t smem = S16_TAB_BYTES + warps * union_warp_smem_bytes(b->max_terms);
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
+    if (orc != DS2I_OK) return orc;
     if (per_sm < 1) return fail(DS2I_E_CUDA, "union kernel does not fit on an SM");
     int grid = per_sm * ix->sm_count;
     int needed = int((b->n_un_items + warps - 1) / warps);
@@ -560,15 +587,10 @@ extern "C" int ds2i_gpu_batch_device_results(ds2i_gpu_batch* b, void** d_counts,
 
 extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { delete b; }
 
-static double now_ms() {
-    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
-
 extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int op, uint32_t k,
                                     const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
                                     uint64_t* out_counts, float* out_scores, float* out_elapsed_ms) {
-    static const bool trace = getenv("DS2I_GPU_TRACE") != nullptr;
+    const bool trace = trace_on();
     double t0 = now_ms();
     ds2i_gpu_batch* b = nullptr;
     unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE) ? 2u : 0u;

@@ -222,54 +222,63 @@ __global__ void __launch_bounds__(128) pef_query_kernel(PefIndexDev idx, DevWand
     run_queries<PefEnum, OP>(idx, wand, batch, k, slots, 0);
 }
 
+struct PefDecodeItem { uint32_t list_pos, part /* bit 31: freqs sequence */, first, count; };   // elements [first, first+count) of one partition
+
 struct PefDecodeJob {
     const uint32_t* terms;
-    const uint64_t* part_prefix;   // nterms+1: (docs partitions + freqs partitions) before list i
+    const PefDecodeItem* items;
     const uint64_t* out_offsets;
     uint32_t* out_docs;
     uint32_t* out_freqs;
-    uint64_t total_parts;
-    uint32_t nterms;
+    uint32_t nitems;
 };
 
-// full decode: one warp per partition (docs partitions first, then freqs partitions of each list)
+// full decode: one warp per item = up to PEF_ITEM_ELEMS consecutive elements of one partition (long
+// partitions — e.g. the single-partition freqs sequence of a long list — are cut so that no warp walks
+// thousands of chunks alone)
+constexpr uint32_t PEF_ITEM_ELEMS = 2048;
+
 static __global__ void __launch_bounds__(256) pef_decode_kernel(PefIndexDev idx, PefDecodeJob job) {
-    uint32_t* buf = smem_words((threadIdx.x >> 5) * 512);
+    uint32_t* buf = smem_words((threadIdx.x >> 5) * 1024);
     const unsigned lane = lane_id();
-    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
-    for (uint64_t g = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); g < job.total_parts; g += nwarps) {
-        uint32_t lo = 0, hi = job.nterms;
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (job.part_prefix[mid] <= g) lo = mid; else hi = mid; }
-        const uint32_t term = job.terms[lo];
-        uint32_t pi = uint32_t(g - job.part_prefix[lo]);
-        const PefListDir d = idx.docs.lists[term], f = idx.freqs.lists[term];
-        const uint64_t o = job.out_offsets[lo];
-        if (pi < d.nparts) {
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < job.nitems; g += nwarps) {
+        const PefDecodeItem it = job.items[g];
+        const uint32_t term = job.terms[it.list_pos];
+        const uint64_t o = job.out_offsets[it.list_pos];
+        const bool is_freq = it.part >> 31;
+        const uint32_t pi = it.part & 0x7fffffffu;
+        if (!is_freq) {
+            const PefListDir d = idx.docs.lists[term];
             PefPart p = PefEnum::load_part(idx.docs.parts, d.first_part + pi);
             PefBody b = pef_open_body(idx.docs, p, false);
-            for (uint32_t i0 = 0; i0 < p.size; i0 += 128) {
-                uint32_t cnt = min(128u, p.size - i0);
+            for (uint32_t i0 = it.first; i0 < it.first + it.count; i0 += 128) {
+                uint32_t cnt = min(128u, it.first + it.count - i0);
                 pef_decode_range(idx.docs, p, b, i0, cnt, buf);
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j) { uint32_t e = lane + 32u * j; if (e < cnt) job.out_docs[o + p.begin + i0 + e] = buf[e]; }
                 __syncwarp();
             }
         } else {
-            pi -= d.nparts;
+            const PefListDir f = idx.freqs.lists[term];
             PefPart p = PefEnum::load_part(idx.freqs.parts, f.first_part + pi);
             PefBody b = pef_open_body(idx.freqs, p, true);
-            uint32_t prev = pi ? p.base - 1u : 0u;       // prefix sum before the partition's first element
-            for (uint32_t i0 = 0; i0 < p.size; i0 += 128) {
-                uint32_t cnt = min(128u, p.size - i0);
-                pef_decode_range(idx.freqs, p, b, i0, cnt, buf);
-                uint32_t last = buf[cnt - 1];
+            // prefix sums c[i]; freq[i] = c[i] - c[i-1]: every chunk is decoded from one element earlier
+            for (uint32_t i0 = it.first; i0 < it.first + it.count; i0 += 127) {
+                uint32_t cnt = min(127u, it.first + it.count - i0);
+                uint32_t ls = i0 ? i0 - 1 : 0;                 // first decoded local index
+                uint32_t n = cnt + (i0 - ls);
+                pef_decode_range(idx.freqs, p, b, ls, n, buf);
+                uint32_t prev0 = pi ? p.base - 1u : 0u;         // prefix sum before the partition's first element
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j) {
                     uint32_t e = lane + 32u * j;
-                    if (e < cnt) job.out_freqs[o + p.begin + i0 + e] = buf[e] - (e ? buf[e - 1] : prev);
+                    if (e < cnt) {
+                        uint32_t k = e + (i0 - ls);
+                        job.out_freqs[o + p.begin + i0 + e] = buf[k] - (k ? buf[k - 1] : prev0);
+                    }
                 }
                 __syncwarp();
-                prev = last;
             }
         }
     }
@@ -477,19 +486,30 @@ inline int pef_launch_query(PefIndexHost& ix, DevWand wand, DevBatch const& db, 
     return -1;
 }
 
-// d_terms / d_offsets are device arrays; partitions are counted on the host from the directory
+// d_terms / d_offsets are device arrays; work items are cut on the host from the partition directory
 inline int pef_decode_lists(PefIndexHost& ix, const uint32_t* h_terms, const uint32_t* d_terms, uint32_t nterms, const uint64_t* d_offsets,
                             uint32_t* d_docs, uint32_t* d_freqs, int sm_count, std::string& err) {
-    std::vector<uint64_t> prefix(size_t(nterms) + 1, 0);
-    for (uint32_t i = 0; i < nterms; ++i) prefix[i + 1] = prefix[i] + ix.docs.lists[h_terms[i]].nparts + ix.freqs.lists[h_terms[i]].nparts;
-    uint64_t* d_prefix = nullptr;
-    if (cudaMalloc(reinterpret_cast<void**>(&d_prefix), prefix.size() * 8) != cudaSuccess) { err = "cudaMalloc failed"; return -3; }
-    cudaMemcpy(d_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice);
-    PefDecodeJob job{d_terms, d_prefix, d_offsets, d_docs, d_freqs, prefix[nterms], nterms};
-    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((prefix[nterms] + 7) / 8, uint64_t(sm_count) * 8)));
-    pef_decode_kernel<<<grid, 256, 8 * 2048>>>(ix.dev, job);
+    std::vector<PefDecodeItem> items;
+    for (uint32_t i = 0; i < nterms; ++i) {
+        for (int fq = 0; fq < 2; ++fq) {
+            PefSeqHost const& sq = fq ? ix.freqs : ix.docs;
+            PefListDir const& d = sq.lists[h_terms[i]];
+            for (uint32_t pi = 0; pi < d.nparts; ++pi) {
+                uint32_t size = sq.parts[d.first_part + pi].size;
+                for (uint32_t first = 0; first < size; first += PEF_ITEM_ELEMS)
+                    items.push_back(PefDecodeItem{i, pi | (fq ? 0x80000000u : 0u), first, std::min(PEF_ITEM_ELEMS, size - first)});
+            }
+        }
+    }
+    if (items.empty()) return 0;
+    PefDecodeItem* d_items = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&d_items), items.size() * sizeof(PefDecodeItem)) != cudaSuccess) { err = "cudaMalloc failed"; return -3; }
+    cudaMemcpy(d_items, items.data(), items.size() * sizeof(PefDecodeItem), cudaMemcpyHostToDevice);
+    PefDecodeJob job{d_terms, d_items, d_offsets, d_docs, d_freqs, uint32_t(items.size())};
+    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((items.size() + 7) / 8, uint64_t(sm_count) * 8)));
+    pef_decode_kernel<<<grid, 256, 8 * 4096>>>(ix.dev, job);
     cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(d_prefix);
+    cudaFree(d_items);
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return -3; }
     return 0;
 }
