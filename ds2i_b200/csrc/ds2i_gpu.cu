@@ -733,13 +733,19 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
     std::vector<uint32_t> tv(terms, terms + nterms);
     CUDA_TRY(d_terms.upload(tv)); CUDA_TRY(d_blk.upload(blk)); CUDA_TRY(d_offs.upload(offs));
     CUDA_TRY(d_docs.alloc(total)); CUDA_TRY(d_freqs.alloc(total));
+    PefDecodeItem* pef_items = nullptr;
+    uint32_t pef_nitems = 0;
+    if (ix->kind == KIND_PEF && nterms && total) {
+        int prc = pef_decode_prepare(*ix->pef, terms, uint32_t(nterms), &pef_items, &pef_nitems, g_last_error);
+        if (prc) return prc;
+    }
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0));
     int rc = DS2I_OK;
     if (nterms && total) {
         if (ix->kind == KIND_PEF) {
-            rc = pef_decode_lists(*ix->pef, terms, d_terms.p, uint32_t(nterms), d_offs.p, d_docs.p, d_freqs.p, ix->sm_count, g_last_error);
+            pef_decode_launch(*ix->pef, pef_items, pef_nitems, d_terms.p, d_offs.p, d_docs.p, d_freqs.p, ix->sm_count);
         } else {
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
             uint64_t want = (blk[nterms] / 32 + 8) / 8;
@@ -755,6 +761,7 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (pef_items) cudaFree(pef_items);
     if (rc != DS2I_OK) return rc;
     if (out_elapsed_ms) *out_elapsed_ms = ms;
     if (total && out_docs) CUDA_TRY(cudaMemcpy(out_docs, d_docs.p, total * 4, cudaMemcpyDeviceToHost));

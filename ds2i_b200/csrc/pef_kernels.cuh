@@ -486,9 +486,8 @@ inline int pef_launch_query(PefIndexHost& ix, DevWand wand, DevBatch const& db, 
     return -1;
 }
 
-// d_terms / d_offsets are device arrays; work items are cut on the host from the partition directory
-inline int pef_decode_lists(PefIndexHost& ix, const uint32_t* h_terms, const uint32_t* d_terms, uint32_t nterms, const uint64_t* d_offsets,
-                            uint32_t* d_docs, uint32_t* d_freqs, int sm_count, std::string& err) {
+// work items of a full decode, cut on the host from the partition directory and uploaded (outside the timed region)
+inline int pef_decode_prepare(PefIndexHost& ix, const uint32_t* h_terms, uint32_t nterms, PefDecodeItem** d_items, uint32_t* nitems, std::string& err) {
     std::vector<PefDecodeItem> items;
     for (uint32_t i = 0; i < nterms; ++i) {
         for (int fq = 0; fq < 2; ++fq) {
@@ -501,17 +500,20 @@ inline int pef_decode_lists(PefIndexHost& ix, const uint32_t* h_terms, const uin
             }
         }
     }
+    *nitems = uint32_t(items.size());
+    *d_items = nullptr;
     if (items.empty()) return 0;
-    PefDecodeItem* d_items = nullptr;
-    if (cudaMalloc(reinterpret_cast<void**>(&d_items), items.size() * sizeof(PefDecodeItem)) != cudaSuccess) { err = "cudaMalloc failed"; return -3; }
-    cudaMemcpy(d_items, items.data(), items.size() * sizeof(PefDecodeItem), cudaMemcpyHostToDevice);
-    PefDecodeJob job{d_terms, d_items, d_offsets, d_docs, d_freqs, uint32_t(items.size())};
-    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((items.size() + 7) / 8, uint64_t(sm_count) * 8)));
-    pef_decode_kernel<<<grid, 256, 8 * 4096>>>(ix.dev, job);
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(d_items);
-    if (e != cudaSuccess) { err = cudaGetErrorString(e); return -3; }
+    if (cudaMalloc(reinterpret_cast<void**>(d_items), items.size() * sizeof(PefDecodeItem)) != cudaSuccess) { err = "cudaMalloc failed"; return -3; }
+    cudaMemcpy(*d_items, items.data(), items.size() * sizeof(PefDecodeItem), cudaMemcpyHostToDevice);
     return 0;
+}
+
+inline void pef_decode_launch(PefIndexHost& ix, const PefDecodeItem* d_items, uint32_t nitems, const uint32_t* d_terms, const uint64_t* d_offsets,
+                              uint32_t* d_docs, uint32_t* d_freqs, int sm_count) {
+    if (!nitems) return;
+    PefDecodeJob job{d_terms, d_items, d_offsets, d_docs, d_freqs, nitems};
+    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(nitems) + 7) / 8, uint64_t(sm_count) * 8)));
+    pef_decode_kernel<<<grid, 256, 8 * 4096>>>(ix.dev, job);
 }
 
 inline int pef_next_geq(PefIndexHost& ix, const uint32_t* d_terms, uint32_t nlists, const uint64_t* d_bounds, const uint64_t* d_offsets,

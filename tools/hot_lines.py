@@ -33,7 +33,9 @@ for i in range(n):
 tot = sum(int(r[ia]) for r in data) or 1; tots = sum(int(r[isamp]) for r in data) or 1
 print('total %.2f G warp instructions, %d samples' % (tot / 1e9, tots))
 src_cache = {}
-for k, v in agg.most_common(top):
+order = samp.most_common(top) if os.environ.get('BY_SAMPLES') else agg.most_common(top)
+for k, _ in order:
+    v = agg[k]
     text = ''
     if k:
         p = os.path.join(ROOT, 'ds2i_b200', 'csrc', k[0])
