@@ -1,22 +1,26 @@
 // Block-at-a-time conjunctive evaluation: and_query / ranked_and_query (queries.hpp:35-86,322-401)
 // re-thought for a warp.  The reference advances ONE candidate docid at a time through next_geq;
 // here the 128 docids of a block of the shortest list are the candidates, carried 4 per lane, and
-// every other list is probed for all of them at once (block_max search by ballot, 128-wide binary
-// search of the decoded block in shared memory).  Survivors are scored in parallel — BM25 summed in
-// the reference's order (lists by increasing size), so every score is bit-identical — and only
-// scores that beat the running threshold reach the (serial) top-k insert.
+// every other list is probed for all of them at once (block_max search by ballot over the aligned
+// block directory, 128-wide binary search of the decoded block in shared memory).  BM25 is accumulated
+// per candidate in registers as the lists are probed, in the reference's order (lists by increasing
+// size), so every score is bit-identical; only scores that beat the running threshold reach the
+// (serial) top-k insert.
 //
 // Work item = (query, chunk of CH consecutive blocks of its shortest list): heavy queries are spread
 // over many warps, each with a private top-k; merge_items_kernel folds the partial results.  The
 // top-k multiset and the match count do not depend on the evaluation order, so results equal the
 // reference's exactly.
+//
+// Shared memory per warp is kept small (560 B per query term + one staging window + one freqs
+// buffer) and the kernel is instantiated per codec, because the path is instruction-issue bound:
+// resident warps and instruction count are what the throughput follows.
 #pragma once
 #include "query_kernels.cuh"
 
 namespace ds2i_gpu {
 
 constexpr uint32_t AND_CHUNK_BLOCKS = 32;     // blocks of the shortest list per work item
-constexpr int AND_SMALL_TERMS = 0;            // queries up to this many terms run in the high-occupancy launch
 
 struct AndItem { uint32_t query, first_block; };
 
@@ -31,62 +35,164 @@ struct AndJob {
     float* item_scores;        // nitems * k
 };
 
-// first block index in [lo, nblocks) whose block_max >= bound (exists: bound <= last max), together
-// with that block's metadata.  The first probe reads 32 consecutive block_max entries AND the
-// matching block_endpoints in the same step, so in the common short-skip case the block's byte range
-// and base arrive with the probe (one memory round trip instead of two); longer skips finish with a
-// 32-ary search and a separate metadata fetch.
-struct BlockMeta { uint32_t block, e0, e1, prev_max, cur_max; bool have; };
+// per query term: cursor + the decoded docids of the current block
+struct AndList {
+    uint64_t data_off;      // absolute byte offset of the list's block data inside m_lists
+    uint32_t bfirst;        // the list's first entry in the block directory
+    uint32_t nblocks;
+    uint32_t n;
+    uint32_t last_max;      // last docid of the list
+    uint32_t pad0, pad1;
+    // written together by lane 0 after every block decode (one 16-B store)
+    uint32_t cur_block;     // 0xffffffff: not positioned yet
+    uint32_t cur_max;       // last docid of the current block
+    uint32_t cur_end;       // byte offset (from data_off) where the current block ends
+    uint32_t freqs_off;     // offset of the current block's freqs inside the staged window (valid until the next staging)
+    uint32_t docs[BLOCK];   // absolute docids of the current block (0xffffffff beyond its size)
+};
+static_assert(sizeof(AndList) == 48 + 4 * BLOCK, "AndList layout");
 
-__device__ DS2I_DECODE_INLINE BlockMeta find_block(WarpCtx& c, const ListState* s, const uint8_t* maxs, uint32_t lo, uint32_t lo_prev_max, uint32_t bound) {
+struct AndWarp {
+    float qw[MAX_TERMS];
+    uint64_t bar;
+    uint64_t pad;
+};
+
+__host__ __device__ constexpr size_t and_warp_smem_bytes(int slots) {
+    return sizeof(AndWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + STAGE_WORDS * 4 + SCRATCH_WORDS * 4;
+}
+
+// staging window <- bytes [start, end) of m_lists (the enclosing 16-B aligned range, one TMA bulk copy,
+// completion on the warp's mbarrier); returns the offset of `start` inside the window
+__device__ __forceinline__ uint32_t and_stage(const uint8_t* lists, uint64_t start, uint64_t end, uint32_t* stage, uint64_t* bar, uint32_t& phase) {
+    const uint64_t a0 = start & ~uint64_t(15);
+    uint32_t bytes = uint32_t(((end + 15) & ~uint64_t(15)) - a0);
+    if (bytes > STAGE_BYTES) bytes = STAGE_BYTES;
+    __syncwarp();   // every lane is done reading the previous window
+    if (bytes) {
+        if (lane_id() == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(stage, lists + a0, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    }
+    return uint32_t(start - a0);
+}
+
+template <int CODEC>
+__device__ __forceinline__ uint32_t and_decode_values(uint32_t stage_off, uint32_t off, uint32_t size, uint32_t sum_of_values, uint32_t out_off,
+                                                      uint32_t stack_off, bool& prefix_out) {
+    if (CODEC != CODEC_INTERPOLATIVE && size == BLOCK) {
+        prefix_out = false;
+        if (CODEC == CODEC_OPTPFOR) return decode_optpfor128(stage_off, off, out_off, stack_off);
+        if (CODEC == CODEC_VARINT) return decode_varint128(stage_off, off, out_off);
+        return decode_qmx128(stage_off, off, out_off);
+    }
+    // n < block_size => every codec falls back to interpolative (block_codecs.hpp:196-199,215-217)
+    prefix_out = true;
+    return decode_interpolative_prefix(stage_off, off, size, sum_of_values, out_off, stack_off);
+}
+
+struct AndCtx {             // warp-uniform registers
+    const uint8_t* lists;
+    uint32_t* stage;
+    uint64_t* bar;
+    uint32_t stage_off, stack_off, ftmp_off;
+    uint32_t phase;
+    // algorithmic-work counters
+    uint32_t c_docs_blocks, c_freqs_blocks, c_bytes_docs, c_bytes_freqs, c_maxs, c_scored;
+};
+
+// block_posting_list.hpp:292-319 with the block's metadata in hand: [e0, e1) = byte range of the block
+// pair inside the list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
+template <int CODEC>
+__device__ __forceinline__ void and_decode_docs(AndCtx& c, AndList* s, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
     const unsigned lane = lane_id();
-    const uint32_t nblocks = s->nblocks;
-    const uint8_t* ends = maxs + 4ull * nblocks;
-    BlockMeta r;
-    {
-        uint32_t bi = lo + lane;
-        uint32_t m = bi < nblocks ? ldg_u32_unaligned(maxs + 4ull * bi) : 0xffffffffu;
-        uint32_t e = (bi < nblocks && bi) ? ldg_u32_unaligned(ends + 4ull * bi - 4ull) : 0u;    // start of block bi
-        unsigned hit = __ballot_sync(FULL, m >= bound);
-        c.c_maxs += 32;
-        if (hit) {
-            uint32_t f = __ffs(hit) - 1;
-            r.block = lo + f;
-            r.cur_max = __shfl_sync(FULL, m, f);
-            r.e0 = __shfl_sync(FULL, e, f);
-            uint32_t pm = __shfl_sync(FULL, m, (f + 31) & 31);
-            r.prev_max = f ? pm : lo_prev_max;
-            uint32_t en = __shfl_sync(FULL, e, (f + 1) & 31);
-            r.have = true;
-            if (r.block + 1 >= nblocks) r.e1 = s->data_bytes;
-            else if (f < 31) r.e1 = en;
-            else r.have = false;          // end offset not among the 32 probed entries
-            return r;
+    const uint32_t n = s->n;
+    const uint32_t cur_base = prev_max + 1u;
+    const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
+    const uint64_t data_off = s->data_off;
+    const uint32_t off = and_stage(c.lists, data_off + e0, data_off + e1, c.stage, c.bar, c.phase);
+    bool prefix;
+    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, off, size, cur_max - cur_base - (size - 1u), smem_offset(s->docs), c.stack_off, prefix);
+    if (prefix) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t i = 32 * j + lane;
+            s->docs[i] = i < size ? cur_base + s->docs[i] + i : 0xffffffffu;
         }
-        lo += 32;
+    } else {
+        uint4 v = reinterpret_cast<uint4*>(s->docs)[lane];
+        v.y += v.x; v.z += v.y; v.w += v.z;
+        const uint32_t incl = warp_inclusive_scan(v.w);
+        const uint32_t add = cur_base + (incl - v.w) + 4u * lane;     // docid_i = base + sum_{k<=i} gap_k + i
+        v.x += add; v.y += add + 1u; v.z += add + 2u; v.w += add + 3u;
+        reinterpret_cast<uint4*>(s->docs)[lane] = v;
     }
-    uint32_t hi = nblocks - 1;          // invariant: max[hi] >= bound, every block < lo has max < bound
-    while (hi - lo >= 32) {
-        uint32_t span = hi - lo;
-        uint32_t probe = lo + uint32_t((uint64_t(span) * (lane + 1)) / 33);
-        uint32_t m = ldg_u32_unaligned(maxs + 4ull * probe);
-        unsigned hit = __ballot_sync(FULL, m >= bound);
-        c.c_maxs += 32;
-        if (hit) {
-            uint32_t f = __ffs(hit) - 1;
-            uint32_t nh = __shfl_sync(FULL, probe, f);
-            if (f > 0) lo = __shfl_sync(FULL, probe, f - 1) + 1;
-            hi = nh;
-        } else {
-            lo = __shfl_sync(FULL, probe, 31) + 1;
-        }
-    }
+    if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, e1, off + consumed);
+    __syncwarp();
+    c.c_docs_blocks += 1; c.c_bytes_docs += consumed;
+}
+
+// freqs - 1 of the current block of `s` -> the warp's freqs buffer (the block pair is still staged);
+// returns whether the buffer holds prefix sums (interpolative) instead of plain values
+template <int CODEC>
+__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const AndList* s, bool count) {
+    const uint32_t n = s->n, b = s->cur_block;
+    const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
+    bool prefix;
+    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, s->freqs_off, size, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
+    if (count) { c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed; }
+    return prefix;
+}
+
+// first block index in [lo, nblocks) whose block_max >= bound (exists: bound <= last max), together
+// with that block's metadata.  One 8-B aligned load per lane reads 32 consecutive (block_max,
+// block_end) directory entries, so in the common short-skip case the block's byte range and base
+// arrive with the probe; longer skips run a 32-ary search first.
+struct BlockMeta { uint32_t block, e0, e1, prev_max, cur_max; };
+
+__device__ __forceinline__ BlockMeta and_find_block(AndCtx& c, const uint2* bd, uint32_t nblocks, uint32_t lo, uint32_t lo_prev_max, uint32_t lo_prev_end,
+                                                    uint32_t bound) {
+    const unsigned lane = lane_id();
     uint32_t bi = lo + lane;
-    uint32_t m = bi <= hi ? ldg_u32_unaligned(maxs + 4ull * bi) : 0xffffffffu;
-    unsigned hit = __ballot_sync(FULL, m >= bound);
-    c.c_maxs += hi - lo + 1;
-    r.block = lo + (__ffs(hit) - 1);
-    r.have = false; r.e0 = r.e1 = r.prev_max = r.cur_max = 0;
+    uint2 en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
+    unsigned hit = __ballot_sync(FULL, en.x >= bound);
+    c.c_maxs += 32;
+    if (!hit) {
+        uint32_t l2 = lo + 32, hi = nblocks - 1;     // invariant: max[hi] >= bound, every block < l2 has max < bound
+        while (hi - l2 >= 31) {
+            const uint32_t span = hi - l2;
+            const uint32_t probe = l2 + uint32_t((uint64_t(span) * (lane + 1)) / 33);
+            const uint32_t m = __ldg(bd + probe).x;
+            const unsigned h = __ballot_sync(FULL, m >= bound);
+            c.c_maxs += 32;
+            if (h) {
+                const uint32_t f = __ffs(h) - 1;
+                const uint32_t nh = __shfl_sync(FULL, probe, f);
+                if (f > 0) l2 = __shfl_sync(FULL, probe, f - 1) + 1;
+                hi = nh;
+            } else {
+                l2 = __shfl_sync(FULL, probe, 31) + 1;
+            }
+        }
+        // the answer lies in [l2, l2 + 30]; window from l2 - 1 so that its predecessor's entry comes along
+        lo = l2 - 1;
+        bi = lo + lane;
+        en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
+        hit = __ballot_sync(FULL, en.x >= bound) & ~1u;
+        c.c_maxs += 32;
+    }
+    const uint32_t f = __ffs(hit) - 1;
+    BlockMeta r;
+    r.block = lo + f;
+    r.cur_max = __shfl_sync(FULL, en.x, f);
+    r.e1 = __shfl_sync(FULL, en.y, f);
+    const uint32_t pm = __shfl_sync(FULL, en.x, (f + 31) & 31);
+    const uint32_t pe = __shfl_sync(FULL, en.y, (f + 31) & 31);
+    r.prev_max = f ? pm : lo_prev_max;
+    r.e0 = f ? pe : lo_prev_end;
     return r;
 }
 
@@ -100,21 +206,26 @@ __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* d, uint32_t x
 }
 
 template <int CODEC, bool RANKED>
-__global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
+__global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
     s16_table_init(smem_words(0));
     __syncthreads();
 
-    typedef BlockEnum<CODEC> E;
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    uint8_t* base = g_smem + S16_TAB_BYTES + warp * warp_smem_bytes(slots);
-    WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
-    ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
-    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState));
-    uint32_t* scratch = stage + STAGE_WORDS;
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * and_warp_smem_bytes(slots);
+    AndWarp* ws = reinterpret_cast<AndWarp*>(base);
+    AndList* st = reinterpret_cast<AndList*>(base + sizeof(AndWarp));
+    uint32_t* ftmp = reinterpret_cast<uint32_t*>(base + sizeof(AndWarp) + size_t(slots) * sizeof(AndList));
+    uint32_t* stage = ftmp + BLOCK;
+    uint32_t* stack = stage + STAGE_WORDS;
 
-    WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar, idx.codec);
+    AndCtx c;
+    c.lists = idx.lists; c.stage = stage; c.bar = &ws->bar;
+    c.stage_off = smem_offset(stage); c.stack_off = smem_offset(stack); c.ftmp_off = smem_offset(ftmp);
+    c.phase = 0;
+    c.c_docs_blocks = c.c_freqs_blocks = c.c_bytes_docs = c.c_bytes_freqs = c.c_maxs = c.c_scored = 0;
+    if (lane == 0) { mbar_init(c.bar, 1); fence_mbar_init(); }
+    __syncwarp();
 
     while (true) {
         uint32_t ii = 0;
@@ -133,76 +244,90 @@ __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wa
         // slot i <- i-th list by increasing size (queries.hpp:357-360, the reference's own std::sort order)
         __syncwarp();
         if (lane < nt) {
-            uint32_t src = batch.ord_size[t0 + lane];
+            const uint32_t src = batch.ord_size[t0 + lane];
             if (RANKED) ws->qw[lane] = batch.q_weight[t0 + src];
-            ListDir d = idx.dir[batch.term[t0 + src]];
-            uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-            ListState* s = &st[lane];
-            s->maxs_off = d.maxs_off;
+            const uint32_t term = batch.term[t0 + src];
+            const ListDir d = idx.dir[term];
+            const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+            const uint32_t bfirst = idx.bfirst[term];
+            AndList* s = &st[lane];
             s->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
-            s->n = d.n; s->nblocks = nblocks; s->data_bytes = d.data_bytes;
+            s->bfirst = bfirst; s->nblocks = nblocks; s->n = d.n;
+            s->last_max = __ldg(idx.bdir + bfirst + nblocks - 1).x;
             s->cur_block = 0xffffffffu;     // not positioned yet
-            s->cur_max = 0;
-            s->pad = ldg_u32_unaligned(idx.lists + d.maxs_off + 4ull * (nblocks - 1));   // last docid of the list
+            s->cur_max = 0; s->cur_end = 0; s->freqs_off = 0;
         }
         __syncwarp();
 
         const uint32_t nb0 = st[0].nblocks;
         const uint32_t b_end = min(nb0, item.first_block + job.chunk_blocks);
-        // metadata of the whole chunk of the driving list, one block per lane, fetched in one round trip
-        uint32_t m_max = 0, m_start = 0, m_end = 0, m_first_prev;
+        // directory entries of the whole chunk of the driving list, one block per lane, in one round trip
+        uint32_t m_max = 0, m_end = 0, first_prev_max = 0xffffffffu, first_prev_end = 0;
         {
             static_assert(AND_CHUNK_BLOCKS <= 32, "one lane per block of the chunk");
-            const uint8_t* maxs0 = idx.lists + st[0].maxs_off;
-            const uint8_t* ends0 = maxs0 + 4ull * nb0;
-            uint32_t bi = item.first_block + lane;
-            if (bi < b_end) {
-                m_max = ldg_u32_unaligned(maxs0 + 4ull * bi);
-                m_start = bi ? ldg_u32_unaligned(ends0 + 4ull * bi - 4ull) : 0u;
-                m_end = bi + 1 < nb0 ? ldg_u32_unaligned(ends0 + 4ull * bi) : st[0].data_bytes;
+            const uint2* bd0 = idx.bdir + st[0].bfirst;
+            const uint32_t bi = item.first_block + lane;
+            if (bi < b_end) { const uint2 en = __ldg(bd0 + bi); m_max = en.x; m_end = en.y; }
+            if (item.first_block) {
+                const uint2 en = __ldg(bd0 + item.first_block - 1);
+                first_prev_max = en.x; first_prev_end = en.y;
             }
-            uint32_t pm = (lane == 0 && item.first_block) ? ldg_u32_unaligned(maxs0 + 4ull * item.first_block - 4ull) : 0xffffffffu;
-            m_first_prev = __shfl_sync(FULL, pm, 0);
         }
         bool exhausted = false;
         for (uint32_t b0 = item.first_block; b0 < b_end && !exhausted; ++b0) {
             {
-                uint32_t l = b0 - item.first_block;
-                uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31);
-                E::decode_docs_block_meta(c, idx, &st[0], b0, __shfl_sync(FULL, m_start, l), __shfl_sync(FULL, m_end, l),
-                                          l ? pm : m_first_prev, __shfl_sync(FULL, m_max, l));
+                const uint32_t l = b0 - item.first_block;
+                const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
+                and_decode_docs<CODEC>(c, &st[0], b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
+                                       __shfl_sync(FULL, m_max, l));
             }
-            if (b0 + 1 < nb0) prefetch_l2(idx.lists + st[0].data_off + st[0].block_end + lane * 32u);   // next block of the driving list
-            uint4 cv = reinterpret_cast<const uint4*>(st[0].docs)[lane];
-            uint32_t cand[4] = {cv.x, cv.y, cv.z, cv.w};
+            const uint4 cv = reinterpret_cast<const uint4*>(st[0].docs)[lane];
+            const uint32_t cand[4] = {cv.x, cv.y, cv.z, cv.w};
             uint32_t alive = 0;            // bit j: candidate 4*lane+j still matches every list probed so far
 #pragma unroll
             for (int j = 0; j < 4; ++j) alive |= (cand[j] != 0xffffffffu) << j;
 
+            // the driving list's own freqs (the block pair is staged right now), kept in registers
+            uint32_t f0[4] = {0, 0, 0, 0};
+            float norm_len[4] = {0.f, 0.f, 0.f, 0.f}, score[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t f0_bytes = 0;
+            if (RANKED) {
+                const uint32_t before = c.c_bytes_freqs;
+                const bool prefix = and_decode_freqs<CODEC>(c, &st[0], true);
+                f0_bytes = c.c_bytes_freqs - before;
+                const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
+                f0[0] = fv.x; f0[1] = fv.y; f0[2] = fv.z; f0[3] = fv.w;
+                if (prefix) {
+                    const uint32_t prev = lane ? ftmp[4 * lane - 1] : 0u;
+                    f0[3] -= f0[2]; f0[2] -= f0[1]; f0[1] -= f0[0]; f0[0] -= prev;
+                }
+                __syncwarp();
+            }
+
             for (uint32_t i = 1; i < nt; ++i) {
                 if (!__any_sync(FULL, alive)) break;
-                ListState* s = &st[i];
-                const uint8_t* maxs = idx.lists + s->maxs_off;
-                const uint32_t last_max = s->pad;
+                AndList* s = &st[i];
+                const uint2* bd = idx.bdir + s->bfirst;
+                const uint32_t last_max = s->last_max;
+                const float qwi = RANKED ? ws->qw[i] : 0.f;
                 uint32_t pending = alive;  // alive candidates not yet looked up in list i
                 while (true) {
                     uint32_t mine = 0xffffffffu;
 #pragma unroll
                     for (int j = 3; j >= 0; --j) if (pending & (1u << j)) mine = cand[j];
-                    uint32_t cmin = __reduce_min_sync(FULL, mine);
+                    const uint32_t cmin = __reduce_min_sync(FULL, mine);
                     if (cmin == 0xffffffffu) break;
                     if (cmin > last_max) {            // list i has nothing at or beyond cmin: those candidates die
                         alive &= ~pending;
-                        // later blocks of list 0 only hold larger docids
-                        exhausted = true;
+                        exhausted = true;             // later blocks of list 0 only hold larger docids
                         break;
                     }
-                    uint32_t cur_block = s->cur_block;
+                    const uint32_t cur_block = s->cur_block;
                     if (cur_block == 0xffffffffu || cmin > s->cur_max) {
-                        bool fresh = cur_block == 0xffffffffu;
-                        BlockMeta bm = find_block(c, s, maxs, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max, cmin);
-                        if (bm.have) E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
-                        else E::decode_docs_block(c, idx, s, bm.block);
+                        const bool fresh = cur_block == 0xffffffffu;
+                        const BlockMeta bm = and_find_block(c, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
+                                                            fresh ? 0u : s->cur_end, cmin);
+                        and_decode_docs<CODEC>(c, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
                     }
                     const uint32_t cur_max = s->cur_max;
                     const uint32_t* d = s->docs;
@@ -218,61 +343,55 @@ __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wa
                         }
                     }
                     if (RANKED && __any_sync(FULL, hitmask)) {
-                        // freqs of this block: decoded into list 0's (otherwise idle) freqs buffer, the
-                        // matched ones parked in list i's buffer under the candidate's slot
-                        uint32_t* ftmp = st[0].freqs;
-                        uint32_t off = stage_range(c, idx.lists, s->data_off + s->freqs_off, s->data_off + s->block_end);
-                        bool prefix;
-                        uint32_t size = s->cur_size;
-                        uint32_t consumed = decode_values<CODEC>(c, off, size, 0xffffffffu, ftmp, prefix);
-                        c.c_freqs_blocks += 1; c.c_freqs_bytes += consumed;
+                        if (i == 1) {
+                            // first term of the sum (queries.hpp:374-379): the driving list's own weight; the
+                            // norm_len gather is in flight while the freqs block is decoded
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (hitmask & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
+                        }
+                        const bool prefix = and_decode_freqs<CODEC>(c, s, true);
+                        const float qw0 = ws->qw[0];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (hitmask & (1u << j)) {
-                                uint32_t p = pos[j];
-                                uint32_t f = prefix ? ftmp[p] - (p ? ftmp[p - 1] : 0u) : ftmp[p];
-                                s->freqs[4 * lane + j] = f;
+                                const uint32_t p = pos[j];
+                                const uint32_t f = prefix ? ftmp[p] - (p ? ftmp[p - 1] : 0u) : ftmp[p];
+                                if (i == 1) score[j] = qw0 * doc_term_weight(f0[j] + 1u, norm_len[j]);
+                                score[j] += qwi * doc_term_weight(f + 1u, norm_len[j]);
                             }
                         __syncwarp();
                     }
                 }
             }
 
-            unsigned nalive = __popc(alive);
-            unsigned total = __reduce_add_sync(FULL, nalive);
+            const unsigned nalive = __popc(alive);
+            const unsigned total = __reduce_add_sync(FULL, nalive);
             matches += total;
-            if (RANKED && total) {
-                // the driving list's own freqs, then BM25 in list order (queries.hpp:374-379)
-                ListState* s0 = &st[0];
-                uint32_t off = stage_range(c, idx.lists, s0->data_off + s0->freqs_off, s0->data_off + s0->block_end);
-                bool prefix;
-                uint32_t consumed = decode_values<CODEC>(c, off, s0->cur_size, 0xffffffffu, s0->freqs, prefix);
-                c.c_freqs_blocks += 1; c.c_freqs_bytes += consumed;
-                c.c_scored += total;
-                float score[4];
+            if (RANKED) {
+                if (!total) {
+                    // the reference never decodes the freqs of a block without a match: not algorithmic work
+                    c.c_freqs_blocks -= 1; c.c_bytes_freqs -= f0_bytes;
+                } else {
+                    c.c_scored += total;
+                    if (nt == 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    score[j] = 0.f;
-                    if (alive & (1u << j)) {
-                        uint32_t slot = 4 * lane + j;
-                        float norm_len = __ldg(wand.norm_lens + cand[j]);
-                        uint32_t f0 = prefix ? s0->freqs[slot] - (slot ? s0->freqs[slot - 1] : 0u) : s0->freqs[slot];
-                        float sc = 0.f;
-                        sc += ws->qw[0] * doc_term_weight(f0 + 1u, norm_len);
-                        for (uint32_t i = 1; i < nt; ++i) sc += ws->qw[i] * doc_term_weight(st[i].freqs[slot] + 1u, norm_len);
-                        score[j] = sc;
+                        for (int j = 0; j < 4; ++j)
+                            if (alive & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
+                        const float qw0 = ws->qw[0];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (alive & (1u << j)) score[j] = qw0 * doc_term_weight(f0[j] + 1u, norm_len[j]);
                     }
-                }
-                __syncwarp();
-                // only scores that can enter the heap are inserted (serially, rare once the threshold is up)
+                    // only scores that can enter the heap are inserted (serially, rare once the threshold is up)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    unsigned want = __ballot_sync(FULL, (alive & (1u << j)) && topk.would_enter(score[j]));
-                    while (want) {
-                        int src = __ffs(want) - 1;
-                        want &= want - 1;
-                        float sc = __shfl_sync(FULL, score[j], src);
-                        topk.insert(sc);
+                    for (int j = 0; j < 4; ++j) {
+                        unsigned want = __ballot_sync(FULL, (alive & (1u << j)) && topk.would_enter(score[j]));
+                        while (want) {
+                            const int src = __ffs(want) - 1;
+                            want &= want - 1;
+                            topk.insert(__shfl_sync(FULL, score[j], src));
+                        }
                     }
                 }
             }
@@ -285,8 +404,8 @@ __global__ void __launch_bounds__(128) and_block_kernel(DevIndex idx, DevWand wa
     if (batch.stats && lane == 0) {
         atomicAdd(&batch.stats[0], (unsigned long long)c.c_docs_blocks);
         atomicAdd(&batch.stats[1], (unsigned long long)c.c_freqs_blocks);
-        atomicAdd(&batch.stats[2], (unsigned long long)c.c_docs_bytes);
-        atomicAdd(&batch.stats[3], (unsigned long long)c.c_freqs_bytes);
+        atomicAdd(&batch.stats[2], (unsigned long long)c.c_bytes_docs);
+        atomicAdd(&batch.stats[3], (unsigned long long)c.c_bytes_freqs);
         atomicAdd(&batch.stats[4], (unsigned long long)c.c_maxs);
         atomicAdd(&batch.stats[5], (unsigned long long)c.c_scored);
     }

@@ -12,7 +12,7 @@ namespace ds2i_gpu {
 enum : int { CODEC_OPTPFOR = 0, CODEC_VARINT = 1, CODEC_INTERPOLATIVE = 2, CODEC_QMX = 3, CODEC_ANY = 99 /* decided at run time from the index */ };
 
 constexpr uint32_t BLOCK = 128;            // BlockCodec::block_size for every codec
-constexpr uint32_t SCRATCH_WORDS = 320;    // Simple16 output (<= 2*128 + 27) / interpolative stack
+constexpr uint32_t SCRATCH_WORDS = 32;     // interpolative stack: <= 7 pending right halves x 4 words
 
 // ---- Simple16 layouts (FastPFor/headers/simple16.h:730-1110) ----------------------------------
 // selector -> up to three runs (count, bits); values fill the 28 payload bits MSB-first.
@@ -67,15 +67,15 @@ __device__ __forceinline__ uint32_t vbyte_decode(const uint32_t* win, uint32_t& 
 
 // ---- OptPFD / NewPFD block of exactly 128 values (FastPFor/headers/newpfor.h:254-286) ---------
 // Header word b<<26 | nExc<<16 | excWords; Simple16 exception stream; 4 groups of 32 values packed
-// LSB-first at b bits (bitpackinghelpers.h fastunpack).  Lane l unpacks element l of each group;
-// the byte phase of the (unaligned) block is folded into the bit position, so no realignment pass.
-// Exceptions: the Simple16 words sit one per lane; every lane locates the word holding "its" two
-// values (position gap e and high bits nExc+e) with a 5-step shuffle search over the scanned
-// per-word counts and extracts them with one table lookup each — no per-word expansion loop.
-__device__ __noinline__ uint32_t decode_optpfor128(uint32_t win_off, uint32_t off, uint32_t out_off, uint32_t scratch_off) {
+// LSB-first at b bits (bitpackinghelpers.h fastunpack).  Lane l unpacks values 4l..4l+3 (one funnel
+// shift when b <= 8); the byte phase of the (unaligned) block is folded into the bit position, so no
+// realignment pass.  Exceptions: the Simple16 words sit one per lane; every lane locates the word
+// holding "its" two values (position gap e and high bits nExc+e) by ranking e in a bitmap of the
+// words' first value indices (two REDUX + a popcount; a shuffle search when there are more than 32
+// exceptions) and extracts them with one table lookup each — no per-word expansion loop.
+__device__ __noinline__ uint32_t decode_optpfor128(uint32_t win_off, uint32_t off, uint32_t out_off, uint32_t /*scratch_off*/) {
     const uint32_t* win = smem_words(win_off);
     uint32_t* out = smem_words(out_off);
-    uint32_t* scratch = smem_words(scratch_off);
     const uint32_t* s16tab = smem_words(0);
     const unsigned lane = lane_id();
     const uint32_t w0 = lds_u32(win, off);
@@ -88,66 +88,94 @@ __device__ __noinline__ uint32_t decode_optpfor128(uint32_t win_off, uint32_t of
         __syncwarp();
         return 4u * 129u;
     }
-    const uint32_t pbit = 8u * (off + 4u * (1u + excw)) + lane * b;
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) out[32 * j + lane] = lds_bits(win, pbit + 32u * b * j, b);
-
+    // the four groups of 32 b-bit values are back to back (b words each): one LSB-first stream of 128
+    // values.  Lane l takes values 4l..4l+3, i.e. the 4b bits at bit 4lb.
+    {
+        const uint32_t pbit = 8u * (off + 4u * (1u + excw)) + 4u * lane * b;
+        uint4 v;
+        if (b <= 8) {
+            const uint32_t w = pbit >> 5;
+            const uint32_t x = __funnelshift_r(win[w], win[w + 1], pbit & 31u);
+            const uint32_t m = (1u << b) - 1u;
+            v.x = x & m; v.y = (x >> b) & m; v.z = (x >> (2u * b)) & m; v.w = (x >> (3u * b)) & m;
+        } else {
+            v.x = lds_bits(win, pbit, b); v.y = lds_bits(win, pbit + b, b);
+            v.z = lds_bits(win, pbit + 2u * b, b); v.w = lds_bits(win, pbit + 3u * b, b);
+        }
+        reinterpret_cast<uint4*>(out)[lane] = v;
+    }
     if (nexc) {
+        __syncwarp();
         if (excw <= 32) {
             const uint32_t word = lane < excw ? lds_u32(win, off + 4u * (1u + lane)) : 0u;
             const uint32_t cnt = lane < excw ? s16tab[word >> 28] : 0u;
             const uint32_t start = warp_inclusive_scan(cnt) - cnt;     // index of this word's first value
-            const uint32_t s_hi = excw > 1 ? 1u << (31 - __clz(excw - 1)) : 0u;   // search steps follow the word count
-            auto fetch = [&](uint32_t e) -> uint32_t {
-                uint32_t w = 0;
-                for (uint32_t s = s_hi; s >= 1; s >>= 1) {
-                    uint32_t st = __shfl_sync(FULL, start, (w + s) & 31u);
-                    if (st <= e) w += s;
-                }
-                uint32_t wv = __shfl_sync(FULL, word, w);
-                uint32_t sv = __shfl_sync(FULL, start, w);
-                uint32_t j = e - sv;
-                return s16_value(s16tab, wv, j < 28u ? j : 0u);
-            };
-            __syncwarp();
-            uint32_t carry = 0;
-            for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
-                uint32_t e = e0 + lane;
-                bool valid = e < nexc;
-                uint32_t g = fetch(valid ? e : 0u) + 1u;
-                uint32_t hi = fetch(valid ? nexc + e : 0u) + 1u;
-                uint32_t incl = warp_inclusive_scan(valid ? g : 0u);
-                uint32_t p = carry + incl - 1u;
+            if (nexc <= 32) {
+                // common case: all 2*nexc <= 64 values.  Two 32-bit maps of the value indices at which a
+                // word starts; the word holding value e is the number of starts <= e, minus one.
+                const bool has = cnt != 0u;
+                const uint32_t bm0 = __reduce_or_sync(FULL, (has && start < 32u) ? 1u << start : 0u);
+                const uint32_t bm1 = __reduce_or_sync(FULL, (has && start >= 32u && start < 64u) ? 1u << (start - 32u) : 0u);
+                const uint32_t pc0 = __popc(bm0);
+                auto fetch = [&](uint32_t e) -> uint32_t {
+                    const bool lo = e < 32u;
+                    const uint32_t m = (lo ? bm0 : bm1) & (0xffffffffu >> (31u - (e & 31u)));
+                    const uint32_t w = __popc(m) + (lo ? 0u : pc0) - 1u;
+                    const uint32_t wv = __shfl_sync(FULL, word, w & 31u);
+                    const uint32_t sv = __shfl_sync(FULL, start, w & 31u);
+                    const uint32_t j = e - sv;
+                    return s16_value(s16tab, wv, j < 28u ? j : 0u);
+                };
+                const bool valid = lane < nexc;
+                const uint32_t g = fetch(valid ? lane : 0u) + 1u;
+                const uint32_t hi = fetch(valid ? nexc + lane : 0u) + 1u;
+                const uint32_t p = warp_inclusive_scan(valid ? g : 0u) - 1u;
                 if (valid && p < BLOCK) out[p] |= hi << b;
-                carry += __shfl_sync(FULL, incl, 31);
-            }
-        } else {
-            // long exception streams (> 32 Simple16 words): expand through shared memory
-            uint32_t* E = scratch;
-            const uint32_t need = 2u * nexc;
-            uint32_t produced = 0;
-            for (uint32_t base = 0; base < excw && produced < need; base += 32) {
-                uint32_t w = base + lane;
-                bool valid = w < excw;
-                uint32_t word = valid ? lds_u32(win, off + 4u * (1u + w)) : 0u;
-                uint32_t cnt = valid ? s16tab[word >> 28] : 0u;
-                uint32_t incl = warp_inclusive_scan(cnt);
-                uint32_t start = produced + incl - cnt;
-                for (uint32_t j = 0; j < cnt; ++j) {
-                    uint32_t idx = start + j;
-                    if (idx < SCRATCH_WORDS) E[idx] = s16_value(s16tab, word, j);
+            } else {
+                const uint32_t s_hi = excw > 1 ? 1u << (31 - __clz(excw - 1)) : 0u;   // search steps follow the word count
+                auto fetch = [&](uint32_t e) -> uint32_t {
+                    uint32_t w = 0;
+                    for (uint32_t s = s_hi; s >= 1; s >>= 1) {
+                        uint32_t st = __shfl_sync(FULL, start, (w + s) & 31u);
+                        if (st <= e) w += s;
+                    }
+                    uint32_t wv = __shfl_sync(FULL, word, w);
+                    uint32_t sv = __shfl_sync(FULL, start, w);
+                    uint32_t j = e - sv;
+                    return s16_value(s16tab, wv, j < 28u ? j : 0u);
+                };
+                uint32_t carry = 0;
+                for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
+                    uint32_t e = e0 + lane;
+                    bool valid = e < nexc;
+                    uint32_t g = fetch(valid ? e : 0u) + 1u;
+                    uint32_t hi = fetch(valid ? nexc + e : 0u) + 1u;
+                    uint32_t incl = warp_inclusive_scan(valid ? g : 0u);
+                    uint32_t p = carry + incl - 1u;
+                    if (valid && p < BLOCK) out[p] |= hi << b;
+                    carry += __shfl_sync(FULL, incl, 31);
                 }
-                produced += __shfl_sync(FULL, incl, 31);
             }
-            __syncwarp();
-            uint32_t carry = 0;
-            for (uint32_t e0 = 0; e0 < nexc; e0 += 32) {
-                uint32_t e = e0 + lane;
-                uint32_t g = e < nexc ? E[e] + 1u : 0u;
-                uint32_t incl = warp_inclusive_scan(g);
-                uint32_t p = carry + incl - 1u;
-                if (e < nexc && p < BLOCK) out[p] |= (E[nexc + e] + 1u) << b;
-                carry += __shfl_sync(FULL, incl, 31);
+        } else if (lane == 0) {
+            // long exception streams (> 32 Simple16 words, practically never): lane 0 walks the two halves
+            // of the value stream (position gaps from value 0, high bits from value nexc) in lock-step
+            const uint32_t wbase = off + 4u;
+            uint32_t wa = 0, ja = 0, wb = 0, jb = 0, skipped = 0;
+            while (true) {
+                uint32_t cw = s16tab[lds_u32(win, wbase + 4u * wb) >> 28];
+                if (skipped + cw > nexc || wb + 1u >= excw) { jb = nexc - skipped; break; }
+                skipped += cw; ++wb;
+            }
+            uint32_t worda = lds_u32(win, wbase), ca = s16tab[worda >> 28];
+            uint32_t wordb = lds_u32(win, wbase + 4u * wb), cb = s16tab[wordb >> 28];
+            uint32_t pos = 0xffffffffu;
+            for (uint32_t e = 0; e < nexc; ++e) {
+                uint32_t g = s16_value(s16tab, worda, ja < 28u ? ja : 0u);
+                if (++ja >= ca) { ++wa; worda = lds_u32(win, wbase + 4u * wa); ca = s16tab[worda >> 28]; ja = 0; }
+                uint32_t h = s16_value(s16tab, wordb, jb < 28u ? jb : 0u);
+                if (++jb >= cb) { ++wb; wordb = wb < excw ? lds_u32(win, wbase + 4u * wb) : 0u; cb = s16tab[wordb >> 28]; jb = 0; }
+                pos += g + 1u;
+                if (pos < BLOCK) out[pos] |= (h + 1u) << b;
             }
         }
     }

@@ -90,12 +90,20 @@ __device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p) {
 }
 
 // ---- warp scans ----------------------------------------------------------------------------------
+// shfl.up's predicate output says whether the source lane exists, so a scan step is two instructions
+// (SHFL.UP + predicated IADD) instead of shuffle + compare + select + add.
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
-    unsigned lane = lane_id();
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL, v, d);
-        if (lane >= unsigned(d)) v += t;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .u32 t;\n"
+            "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+            "@p add.u32 %0, %0, t;\n"
+            "}\n"
+            : "+r"(v)
+            : "r"(d));
     }
     return v;
 }

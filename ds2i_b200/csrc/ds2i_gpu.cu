@@ -462,6 +462,7 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
         uint32_t count = cls == 0 ? b->n_and_items_large : b->n_and_items - b->n_and_items_large;
         if (!count) continue;
         int slots = cls == 0 ? b->max_terms : std::min(b->max_terms, AND_SMALL_TERMS);
+        if (const char* ev = getenv("DS2I_GPU_SLOTS_OVERRIDE")) slots = std::max(slots, atoi(ev));
         size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(slots);
         int per_sm = 0;
         int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
@@ -540,6 +541,9 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
         if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
             if (!ranked) k = 1;
+            if (ix->codec == CODEC_OPTPFOR && getenv("DS2I_GPU_SPECIALIZE"))
+                rc = op == OP_AND ? launch_and_block<CODEC_OPTPFOR, false>(b, db, k) : launch_and_block<CODEC_OPTPFOR, true>(b, db, k);
+            else
             rc = op == OP_AND ? launch_and_block<CODEC_ANY, false>(b, db, k) : launch_and_block<CODEC_ANY, true>(b, db, k);
         }
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u)) {
