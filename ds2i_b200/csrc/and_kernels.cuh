@@ -47,7 +47,7 @@ struct AndList {
     uint32_t cur_block;     // 0xffffffff: not positioned yet
     uint32_t cur_max;       // last docid of the current block
     uint32_t cur_end;       // byte offset (from data_off) where the current block ends
-    uint32_t freqs_off;     // offset of the current block's freqs inside the staged window (valid until the next staging)
+    uint32_t freqs_off;     // byte offset (from data_off) of the current block's freqs
     uint32_t docs[BLOCK];   // absolute docids of the current block (0xffffffff beyond its size)
 };
 static_assert(sizeof(AndList) == 48 + 4 * BLOCK, "AndList layout");
@@ -100,6 +100,8 @@ struct AndCtx {             // warp-uniform registers
     uint64_t* bar;
     uint32_t stage_off, stack_off, ftmp_off;
     uint32_t phase;
+    uint32_t win_slot;      // list slot whose current block pair sits in the staging window (0xffffffff: none)
+    uint32_t win_delta;     // window offset of that list's data byte 0 (mod 2^32)
     // algorithmic-work counters
     uint32_t c_docs_blocks, c_freqs_blocks, c_bytes_docs, c_bytes_freqs, c_maxs, c_scored;
 };
@@ -107,7 +109,7 @@ struct AndCtx {             // warp-uniform registers
 // block_posting_list.hpp:292-319 with the block's metadata in hand: [e0, e1) = byte range of the block
 // pair inside the list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
 template <int CODEC>
-__device__ __forceinline__ void and_decode_docs(AndCtx& c, AndList* s, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
+__device__ __forceinline__ void and_decode_docs(AndCtx& c, AndList* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
     const unsigned lane = lane_id();
     const uint32_t n = s->n;
     const uint32_t cur_base = prev_max + 1u;
@@ -130,20 +132,28 @@ __device__ __forceinline__ void and_decode_docs(AndCtx& c, AndList* s, uint32_t 
         v.x += add; v.y += add + 1u; v.z += add + 2u; v.w += add + 3u;
         reinterpret_cast<uint4*>(s->docs)[lane] = v;
     }
-    if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, e1, off + consumed);
+    if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, e1, e0 + consumed);
     __syncwarp();
+    c.win_slot = slot; c.win_delta = off - e0;
     c.c_docs_blocks += 1; c.c_bytes_docs += consumed;
 }
 
-// freqs - 1 of the current block of `s` -> the warp's freqs buffer (the block pair is still staged);
-// returns whether the buffer holds prefix sums (interpolative) instead of plain values
+// freqs - 1 of the current block of `s` -> the warp's freqs buffer.  Right after the docs decode the
+// block pair is still staged; a block carried over from an earlier candidate batch is staged again.
+// Returns whether the buffer holds prefix sums (interpolative) instead of plain values.
 template <int CODEC>
-__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const AndList* s, bool count) {
+__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const AndList* s, uint32_t slot) {
     const uint32_t n = s->n, b = s->cur_block;
     const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
+    const uint32_t freqs_off = s->freqs_off;
+    if (c.win_slot != slot) {
+        const uint64_t data_off = s->data_off;
+        const uint32_t off = and_stage(c.lists, data_off + freqs_off, data_off + s->cur_end, c.stage, c.bar, c.phase);
+        c.win_slot = slot; c.win_delta = off - freqs_off;
+    }
     bool prefix;
-    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, s->freqs_off, size, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
-    if (count) { c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed; }
+    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, freqs_off + c.win_delta, size, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
+    c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed;
     return prefix;
 }
 
@@ -153,13 +163,13 @@ __device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const AndList* s, bo
 // arrive with the probe; longer skips run a 32-ary search first.
 struct BlockMeta { uint32_t block, e0, e1, prev_max, cur_max; };
 
-__device__ __forceinline__ BlockMeta and_find_block(AndCtx& c, const uint2* bd, uint32_t nblocks, uint32_t lo, uint32_t lo_prev_max, uint32_t lo_prev_end,
+__device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint2* bd, uint32_t nblocks, uint32_t lo, uint32_t lo_prev_max, uint32_t lo_prev_end,
                                                     uint32_t bound) {
     const unsigned lane = lane_id();
     uint32_t bi = lo + lane;
     uint2 en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
     unsigned hit = __ballot_sync(FULL, en.x >= bound);
-    c.c_maxs += 32;
+    c_maxs += 32;
     if (!hit) {
         uint32_t l2 = lo + 32, hi = nblocks - 1;     // invariant: max[hi] >= bound, every block < l2 has max < bound
         while (hi - l2 >= 31) {
@@ -167,7 +177,7 @@ __device__ __forceinline__ BlockMeta and_find_block(AndCtx& c, const uint2* bd, 
             const uint32_t probe = l2 + uint32_t((uint64_t(span) * (lane + 1)) / 33);
             const uint32_t m = __ldg(bd + probe).x;
             const unsigned h = __ballot_sync(FULL, m >= bound);
-            c.c_maxs += 32;
+            c_maxs += 32;
             if (h) {
                 const uint32_t f = __ffs(h) - 1;
                 const uint32_t nh = __shfl_sync(FULL, probe, f);
@@ -182,7 +192,7 @@ __device__ __forceinline__ BlockMeta and_find_block(AndCtx& c, const uint2* bd, 
         bi = lo + lane;
         en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
         hit = __ballot_sync(FULL, en.x >= bound) & ~1u;
-        c.c_maxs += 32;
+        c_maxs += 32;
     }
     const uint32_t f = __ffs(hit) - 1;
     BlockMeta r;
@@ -205,8 +215,8 @@ __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* d, uint32_t x
     return pos;
 }
 
-template <int CODEC, bool RANKED>
-__global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
+template <int CODEC, bool RANKED, int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
     s16_table_init(smem_words(0));
     __syncthreads();
 
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand
     AndCtx c;
     c.lists = idx.lists; c.stage = stage; c.bar = &ws->bar;
     c.stage_off = smem_offset(stage); c.stack_off = smem_offset(stack); c.ftmp_off = smem_offset(ftmp);
-    c.phase = 0;
+    c.phase = 0; c.win_slot = 0xffffffffu; c.win_delta = 0;
     c.c_docs_blocks = c.c_freqs_blocks = c.c_bytes_docs = c.c_bytes_freqs = c.c_maxs = c.c_scored = 0;
     if (lane == 0) { mbar_init(c.bar, 1); fence_mbar_init(); }
     __syncwarp();
@@ -242,6 +252,7 @@ __global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand
         topk.init(k);
 
         // slot i <- i-th list by increasing size (queries.hpp:357-360, the reference's own std::sort order)
+        c.win_slot = 0xffffffffu;
         __syncwarp();
         if (lane < nt) {
             const uint32_t src = batch.ord_size[t0 + lane];
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand
             {
                 const uint32_t l = b0 - item.first_block;
                 const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
-                and_decode_docs<CODEC>(c, &st[0], b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
+                and_decode_docs<CODEC>(c, &st[0], 0u, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
                                        __shfl_sync(FULL, m_max, l));
             }
             const uint4 cv = reinterpret_cast<const uint4*>(st[0].docs)[lane];
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand
             uint32_t f0_bytes = 0;
             if (RANKED) {
                 const uint32_t before = c.c_bytes_freqs;
-                const bool prefix = and_decode_freqs<CODEC>(c, &st[0], true);
+                const bool prefix = and_decode_freqs<CODEC>(c, &st[0], 0u);
                 f0_bytes = c.c_bytes_freqs - before;
                 const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
                 f0[0] = fv.x; f0[1] = fv.y; f0[2] = fv.z; f0[3] = fv.w;
@@ -325,9 +336,9 @@ __global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand
                     const uint32_t cur_block = s->cur_block;
                     if (cur_block == 0xffffffffu || cmin > s->cur_max) {
                         const bool fresh = cur_block == 0xffffffffu;
-                        const BlockMeta bm = and_find_block(c, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
+                        const BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
                                                             fresh ? 0u : s->cur_end, cmin);
-                        and_decode_docs<CODEC>(c, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+                        and_decode_docs<CODEC>(c, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
                     }
                     const uint32_t cur_max = s->cur_max;
                     const uint32_t* d = s->docs;
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(128, 6) and_block_kernel(DevIndex idx, DevWand
                             for (int j = 0; j < 4; ++j)
                                 if (hitmask & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
                         }
-                        const bool prefix = and_decode_freqs<CODEC>(c, s, true);
+                        const bool prefix = and_decode_freqs<CODEC>(c, s, i);
                         const float qw0 = ws->qw[0];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)

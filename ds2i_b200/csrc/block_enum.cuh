@@ -20,6 +20,11 @@ struct ListDir {            // per posting list, built once at load time (host) 
 struct DevIndex {
     const uint8_t* lists;   // m_lists, 256-B aligned device copy with a zeroed tail pad
     const ListDir* dir;
+    // aligned copy of every list's block_maxs[] / block_endpoints[] (byte-aligned only in the file,
+    // block_posting_list.hpp:43,49), built once at load time: entry b of a list = (block_max[b], byte
+    // offset inside the list's block data where block b ends), list t starts at bdir[bfirst[t]]
+    const uint2* bdir;
+    const uint32_t* bfirst;
     uint64_t num_lists;
     uint32_t num_docs;
     int codec;              // CODEC_*
@@ -39,6 +44,8 @@ struct ListState {
     uint32_t last_max;      // last docid of the list
     uint32_t win_block;     // block the list sat on when the current window started
     uint32_t exhausted;
+    uint32_t bfirst;        // the list's first entry in the block directory (DevIndex::bdir)
+    uint32_t pad1, pad2, pad3;
     uint32_t docs[BLOCK];   // absolute docids of the current block (0xffffffff beyond cur_size)
     uint32_t freqs[BLOCK];  // freqs - 1 of the current block, valid when freqs_ready
 };

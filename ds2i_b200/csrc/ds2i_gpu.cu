@@ -98,6 +98,8 @@ struct ds2i_gpu_index {
     std::vector<ListDir> host_dir;
     dev_buf<uint8_t> d_lists;
     dev_buf<ListDir> d_dir;
+    dev_buf<uint2> d_bdir;
+    dev_buf<uint32_t> d_bfirst;
     DevIndex dev{};
     // opt (partitioned Elias-Fano) index
     std::unique_ptr<PefIndexHost> pef;
@@ -128,7 +130,7 @@ struct ds2i_gpu_batch {
     dev_buf<AndItem> and_items;
     dev_buf<uint32_t> and_order, and_item_begin, and_item_counts, and_item_sizes;
     dev_buf<float> and_item_scores;
-    uint32_t n_and_items = 0, n_and_items_large = 0, and_chunk = AND_CHUNK_BLOCKS;
+    uint32_t n_and_items = 0, and_chunk = AND_CHUNK_BLOCKS;
     // block-parallel union path (wand / maxscore): work items = (query, docid range)
     dev_buf<UnionItem> un_items;
     dev_buf<uint32_t> un_order, un_item_begin, un_item_sizes, un_threshold;
@@ -189,6 +191,8 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
         std::vector<uint64_t> starts = ef_decode_all(f.endpoints, 0, f.lists_bytes, f.size, f.params);
         ix->host_dir.resize(f.size);
         const uint8_t* lists_end = f.lists + f.lists_bytes;
+        std::vector<uint2> bdir;
+        std::vector<uint32_t> bfirst(f.size);
         for (uint64_t i = 0; i < f.size; ++i) {
             uint64_t begin = starts[i], end = (i + 1 < f.size) ? starts[i + 1] : f.lists_bytes;
             if (begin >= end || end > f.lists_bytes) throw format_error("list endpoints out of order");
@@ -200,15 +204,28 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
             uint64_t data_off = maxs_off + 4 * blocks + 4 * (blocks - 1);
             if (data_off > end) throw format_error("posting list header exceeds the list");
             ix->host_dir[i] = ListDir{maxs_off, n, uint32_t(end - data_off)};
+            if (bdir.size() + blocks > 0xfffffff0ull) return fail(DS2I_E_LIMIT, "more than 2^32 blocks in the index");
+            bfirst[i] = uint32_t(bdir.size());
+            const uint8_t* maxs = f.lists + maxs_off;
+            const uint8_t* ends = maxs + 4 * blocks;
+            for (uint64_t b = 0; b < blocks; ++b) {
+                uint32_t m, e = uint32_t(end - data_off);
+                memcpy(&m, maxs + 4 * b, 4);
+                if (b + 1 < blocks) memcpy(&e, ends + 4 * b, 4);
+                bdir.push_back(make_uint2(m, e));
+            }
         }
+        bdir.push_back(make_uint2(0xffffffffu, 0u));   // probes may read one entry past the last list
         const size_t pad = 4096;   // staged windows and unaligned reads may run past the last list
         CUDA_TRY(ix->d_lists.alloc(f.lists_bytes + pad));
         CUDA_TRY(cudaMemcpy(ix->d_lists.p, f.lists, f.lists_bytes, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemset(ix->d_lists.p + f.lists_bytes, 0, pad));
         CUDA_TRY(ix->d_dir.upload(ix->host_dir));
-        ix->dev.lists = ix->d_lists.p; ix->dev.dir = ix->d_dir.p;
+        CUDA_TRY(ix->d_bdir.upload(bdir)); CUDA_TRY(ix->d_bfirst.upload(bfirst));
+        CUDA_TRY(cudaStreamSynchronize(0));     // the host vectors go out of scope
+        ix->dev.lists = ix->d_lists.p; ix->dev.dir = ix->d_dir.p; ix->dev.bdir = ix->d_bdir.p; ix->dev.bfirst = ix->d_bfirst.p;
         ix->dev.num_lists = f.size; ix->dev.num_docs = uint32_t(f.num_docs); ix->dev.codec = codec;
-        ix->device_bytes = f.lists_bytes + pad + f.size * sizeof(ListDir);
+        ix->device_bytes = f.lists_bytes + pad + f.size * (sizeof(ListDir) + 4) + bdir.size() * sizeof(uint2);
     } catch (std::exception const& e) {
         return fail(DS2I_E_FORMAT, e.what());
     }
@@ -374,17 +391,10 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         for (uint64_t fb = 0; fb < nb0; fb += and_chunk) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
         item_begin[q + 1] = uint32_t(items.size());
     }
-    // two occupancy classes: queries with few terms run with small per-warp shared memory (more
-    // resident warps); within a class the items of the costliest queries come first
+    // the items of the costliest queries come first
     item_order.reserve(items.size());
-    for (int cls = 0; cls < 2; ++cls) {
-        for (uint32_t qi : sched) {
-            bool small = (q_begin[qi + 1] - q_begin[qi]) <= uint32_t(AND_SMALL_TERMS);
-            if (small != (cls == 1)) continue;
-            for (uint32_t it = item_begin[qi]; it < item_begin[qi + 1]; ++it) item_order.push_back(it);
-        }
-        if (cls == 0) b->n_and_items_large = uint32_t(item_order.size());
-    }
+    for (uint32_t qi : sched)
+        for (uint32_t it = item_begin[qi]; it < item_begin[qi + 1]; ++it) item_order.push_back(it);
     b->n_and_items = uint32_t(items.size());
     CUDA_TRY(b->and_items.upload(items)); CUDA_TRY(b->and_order.upload(item_order)); CUDA_TRY(b->and_item_begin.upload(item_begin));
     CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
@@ -450,34 +460,51 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     return DS2I_OK;
 }
 
-template <int CODEC, bool RANKED>
+constexpr int AND_MIN_CTAS = 6;     // 24 resident warps per SM (<= 80 registers per thread)
+
+template <int CODEC, bool RANKED, int MIN_CTAS = AND_MIN_CTAS>
 static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    auto kern = and_block_kernel<CODEC, RANKED>;
+    auto kern = and_block_kernel<CODEC, RANKED, MIN_CTAS>;
     DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr};
-    // class 0: queries with many terms (slots = the batch maximum); class 1: <= AND_SMALL_TERMS terms
-    for (int cls = 0; cls < 2; ++cls) {
-        uint32_t first = cls == 0 ? 0 : b->n_and_items_large;
-        uint32_t count = cls == 0 ? b->n_and_items_large : b->n_and_items - b->n_and_items_large;
-        if (!count) continue;
-        int slots = cls == 0 ? b->max_terms : std::min(b->max_terms, AND_SMALL_TERMS);
-        if (const char* ev = getenv("DS2I_GPU_SLOTS_OVERRIDE")) slots = std::max(slots, atoi(ev));
-        size_t smem = S16_TAB_BYTES + warps * warp_smem_bytes(slots);
+    if (b->n_and_items) {
+        int slots = b->max_terms;
+        if (const char* ev = getenv("DS2I_GPU_SLOTS_OVERRIDE")) slots = std::max(slots, atoi(ev));     // occupancy experiments
+        size_t smem = S16_TAB_BYTES + warps * and_warp_smem_bytes(slots);
         int per_sm = 0;
         int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
         if (orc != DS2I_OK) return orc;
         if (per_sm < 1) return fail(DS2I_E_CUDA, "conjunctive kernel does not fit on an SM");
         int grid = per_sm * ix->sm_count;
-        int needed = int((count + warps - 1) / warps);
+        int needed = int((b->n_and_items + warps - 1) / warps);
         if (grid > needed) grid = std::max(needed, 1);
-        AndJob job{b->and_items.p, b->and_order.p + first, count, b->and_chunk, b->work_counter.p + 1 + cls, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
+        AndJob job{b->and_items.p, b->and_order.p, b->n_and_items, b->and_chunk, b->work_counter.p + 1, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
         kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, slots);
         b->launches += 1;
     }
     merge_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->and_item_begin.p, b->nq, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p,
                                                  k, RANKED, b->out_counts.p, b->out_scores.p);
     return DS2I_OK;   // the caller counts the merge launch
+}
+
+// the conjunctive kernel is instantiated per codec: the path is issue-bound and a codec-specific
+// instance is a third smaller than one that dispatches at run time
+template <bool RANKED>
+static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
+    switch (b->index->codec) {
+        case CODEC_OPTPFOR:
+            if (const char* ev = getenv("DS2I_GPU_AND_MIN_CTAS")) {      // occupancy experiments
+                if (atoi(ev) == 4) return launch_and_block<CODEC_OPTPFOR, RANKED, 4>(b, db, k);
+                if (atoi(ev) == 5) return launch_and_block<CODEC_OPTPFOR, RANKED, 5>(b, db, k);
+                if (atoi(ev) == 8) return launch_and_block<CODEC_OPTPFOR, RANKED, 8>(b, db, k);
+            }
+            return launch_and_block<CODEC_OPTPFOR, RANKED>(b, db, k);
+        case CODEC_VARINT: return launch_and_block<CODEC_VARINT, RANKED>(b, db, k);
+        case CODEC_INTERPOLATIVE: return launch_and_block<CODEC_INTERPOLATIVE, RANKED>(b, db, k);
+        case CODEC_QMX: return launch_and_block<CODEC_QMX, RANKED>(b, db, k);
+    }
+    return fail(DS2I_E_UNSUPPORTED, "unknown codec");
 }
 
 template <int CODEC>
@@ -541,10 +568,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
         if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
             if (!ranked) k = 1;
-            if (ix->codec == CODEC_OPTPFOR && getenv("DS2I_GPU_SPECIALIZE"))
-                rc = op == OP_AND ? launch_and_block<CODEC_OPTPFOR, false>(b, db, k) : launch_and_block<CODEC_OPTPFOR, true>(b, db, k);
-            else
-            rc = op == OP_AND ? launch_and_block<CODEC_ANY, false>(b, db, k) : launch_and_block<CODEC_ANY, true>(b, db, k);
+            rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k) : launch_and_block_codec<true>(b, db, k);
         }
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u)) {
             rc = launch_union_block<CODEC_ANY>(b, db, k);

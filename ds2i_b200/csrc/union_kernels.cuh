@@ -83,8 +83,9 @@ struct UnionOps {
     }
 
     // essential list: docs + freqs of block b, cursor at its first element
-    static __device__ __forceinline__ void load_essential_block(WarpCtx& c, DevIndex const& idx, ListState* s, uint32_t b) {
-        E::decode_docs_block(c, idx, s, b);
+    static __device__ __forceinline__ void load_essential_block(WarpCtx& c, DevIndex const& idx, ListState* s, BlockMeta const& bm) {
+        E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+        const uint32_t b = bm.block;
         if (b + 1 < s->nblocks) prefetch_l2(idx.lists + s->data_off + s->block_end + lane_id() * 32u);
         decode_freqs_plain(c, idx, s, s->freqs);
         if (lane_id() == 0) s->freqs_ready = 1;
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
             s->n = d.n; s->nblocks = nblocks; s->data_bytes = d.data_bytes;
             s->cur_block = 0xffffffffu; s->cur_max = 0; s->prev_max = 0xffffffffu; s->cur_size = 0; s->pos = 0;
             s->freqs_ready = 0; s->win_block = 0xffffffffu;
-            s->last_max = ldg_u32_unaligned(idx.lists + d.maxs_off + 4ull * (nblocks - 1));
+            s->bfirst = idx.bfirst[batch.term[t0 + src]];
+            s->last_max = __ldg(idx.bdir + s->bfirst + nblocks - 1).x;
             s->exhausted = s->last_max < lo ? 1u : 0u;
         }
         __syncwarp();
@@ -179,8 +181,9 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                 if (cb == 0xffffffffu || s->cur_max < lo) {
                     // never touched (or left behind as a probed list): find the block holding the first docid >= lo
                     bool fresh = cb == 0xffffffffu;
-                    BlockMeta bm = find_block(c, s, idx.lists + s->maxs_off, fresh ? 0u : cb + 1, fresh ? 0xffffffffu : s->cur_max, lo);
-                    U::load_essential_block(c, idx, s, bm.block);
+                    BlockMeta bm = and_find_block(c.c_maxs, idx.bdir + s->bfirst, s->nblocks, fresh ? 0u : cb + 1, fresh ? 0xffffffffu : s->cur_max,
+                                                  fresh ? 0u : s->block_end, lo);
+                    U::load_essential_block(c, idx, s, bm);
                     uint32_t p = U::count_less(s, lo);
                     if (lane == 0) s->pos = p;
                     __syncwarp();
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                     if (!__any_sync(FULL, probing)) break;
                     ListState* s = &st[i];
                     if (s->exhausted) continue;
-                    const uint8_t* maxs = idx.lists + s->maxs_off;
+                    const uint2* bd = idx.bdir + s->bfirst;
                     uint32_t pending = probing;
                     while (true) {
                         uint32_t mine = 0xffffffffu;
@@ -303,9 +306,9 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                         uint32_t cur_block = s->cur_block;
                         if (cur_block == 0xffffffffu || cmin > s->cur_max) {
                             bool fresh = cur_block == 0xffffffffu;
-                            BlockMeta bm = find_block(c, s, maxs, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max, cmin);
-                            if (bm.have) E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
-                            else E::decode_docs_block(c, idx, s, bm.block);
+                            BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
+                                                          fresh ? 0u : s->block_end, cmin);
+                            E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
                         }
                         const uint32_t cur_max = s->cur_max;
                         const uint32_t* d = s->docs;
@@ -357,7 +360,10 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                 if (s->pos >= s->cur_size) {
                     uint32_t nb = s->cur_block + 1;
                     if (nb >= s->nblocks || s->cur_max + 1u >= hi) { __syncwarp(); if (lane == 0) s->exhausted = 1; __syncwarp(); }
-                    else U::load_essential_block(c, idx, s, nb);
+                    else {
+                        const uint2 en = __ldg(idx.bdir + s->bfirst + nb);     // the next block's (block_max, end)
+                        U::load_essential_block(c, idx, s, BlockMeta{nb, s->block_end, en.y, s->cur_max, en.x});
+                    }
                 }
             }
             __syncwarp();
