@@ -108,8 +108,8 @@ struct AndCtx {             // warp-uniform registers
 
 // block_posting_list.hpp:292-319 with the block's metadata in hand: [e0, e1) = byte range of the block
 // pair inside the list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
-template <int CODEC>
-__device__ __forceinline__ void and_decode_docs(AndCtx& c, AndList* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
+template <int CODEC, class List>
+__device__ __forceinline__ void and_decode_docs(AndCtx& c, List* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
     const unsigned lane = lane_id();
     const uint32_t n = s->n;
     const uint32_t cur_base = prev_max + 1u;
@@ -138,11 +138,11 @@ __device__ __forceinline__ void and_decode_docs(AndCtx& c, AndList* s, uint32_t 
     c.c_docs_blocks += 1; c.c_bytes_docs += consumed;
 }
 
-// freqs - 1 of the current block of `s` -> the warp's freqs buffer.  Right after the docs decode the
+// freqs - 1 of the current block of `s` -> the 128-word buffer at out_off.  Right after the docs decode the
 // block pair is still staged; a block carried over from an earlier candidate batch is staged again.
 // Returns whether the buffer holds prefix sums (interpolative) instead of plain values.
-template <int CODEC>
-__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const AndList* s, uint32_t slot) {
+template <int CODEC, class List>
+__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const List* s, uint32_t slot, uint32_t out_off) {
     const uint32_t n = s->n, b = s->cur_block;
     const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
     const uint32_t freqs_off = s->freqs_off;
@@ -152,7 +152,7 @@ __device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const AndList* s, ui
         c.win_slot = slot; c.win_delta = off - freqs_off;
     }
     bool prefix;
-    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, freqs_off + c.win_delta, size, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
+    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, freqs_off + c.win_delta, size, 0xffffffffu, out_off, c.stack_off, prefix);
     c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed;
     return prefix;
 }
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             uint32_t f0_bytes = 0;
             if (RANKED) {
                 const uint32_t before = c.c_bytes_freqs;
-                const bool prefix = and_decode_freqs<CODEC>(c, &st[0], 0u);
+                const bool prefix = and_decode_freqs<CODEC>(c, &st[0], 0u, c.ftmp_off);
                 f0_bytes = c.c_bytes_freqs - before;
                 const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
                 f0[0] = fv.x; f0[1] = fv.y; f0[2] = fv.z; f0[3] = fv.w;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                             for (int j = 0; j < 4; ++j)
                                 if (hitmask & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
                         }
-                        const bool prefix = and_decode_freqs<CODEC>(c, s, i);
+                        const bool prefix = and_decode_freqs<CODEC>(c, s, i, c.ftmp_off);
                         const float qw0 = ws->qw[0];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)

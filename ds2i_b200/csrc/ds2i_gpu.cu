@@ -571,7 +571,13 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
             rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k) : launch_and_block_codec<true>(b, db, k);
         }
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u)) {
-            rc = launch_union_block<CODEC_ANY>(b, db, k);
+            switch (ix->codec) {       // per-codec instances: smaller kernels, fewer instruction-cache misses
+                case CODEC_OPTPFOR: rc = launch_union_block<CODEC_OPTPFOR>(b, db, k); break;
+                case CODEC_VARINT: rc = launch_union_block<CODEC_VARINT>(b, db, k); break;
+                case CODEC_INTERPOLATIVE: rc = launch_union_block<CODEC_INTERPOLATIVE>(b, db, k); break;
+                case CODEC_QMX: rc = launch_union_block<CODEC_QMX>(b, db, k); break;
+                default: rc = fail(DS2I_E_UNSUPPORTED, "unknown codec");
+            }
         }
         else rc = launch_query_op<CODEC_ANY>(b, db, op, k);
         if (rc != DS2I_OK) return rc;

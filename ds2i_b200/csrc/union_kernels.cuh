@@ -7,17 +7,18 @@
 // after every insert — sequential.  This kernel keeps MaxScore's pruning logic (lists sorted by
 // max_weight, prefix sums ub[], "essential" lists whose postings are the only candidates,
 // non-essential lists probed from the highest bound down while score + ub[i] can still enter,
-// queries.hpp:519-578) but evaluates it 128 candidates at a time:
-//   * a window = the docids up to the smallest current block_max of the essential lists; the
-//     postings of each essential list inside the window are candidates, 4 per lane;
-//   * essential contributions: 128-wide binary search of the other essential lists' decoded blocks
-//     (a document is scored by the first essential list that contains it);
-//   * non-essential lists: the block-at-a-time probing of and_kernels.cuh, restricted to the
+// queries.hpp:519-578) but evaluates it a docid TILE at a time:
+//   * tile = UNION_TILE consecutive docids, with one fp32 accumulator per docid in shared memory;
+//   * essential lists, in increasing max_weight order, add q_weight * doc_term_weight of their postings
+//     inside the tile to the accumulators (one list at a time, so every document's sum is formed in
+//     the reference's order, queries.hpp:545-554, without atomics);
+//   * the touched accumulators are the candidates, 128 consecutive docids (4 per lane) per pass;
+//     non-essential lists are probed block-at-a-time as in and_kernels.cuh, restricted to the
 //     candidates for which would_enter(score + ub[i]) still holds;
 //   * only scores above the running threshold reach the serial top-k insert.
-// Pruning with a stale (lower) threshold is always safe, so the top-k multiset equals the
-// reference's; per-document sums follow MaxScore's order (essential lists by increasing max_weight,
-// then non-essential ones downwards) but which lists are essential depends on the threshold
+// Tiles without essential postings are never visited (the next tile is the one holding the smallest
+// unconsumed essential posting).  Pruning with a stale (lower) threshold is always safe, so the
+// top-k multiset equals the reference's; which lists are essential depends on the threshold
 // history, so scores can differ from the reference in the last bit — within the 1e-5 relative
 // tolerance of the north star (the literal, bit-exact kernels stay available: DS2I_RUN_FAITHFUL).
 //
@@ -50,73 +51,91 @@ struct TopKShared {
     __device__ __forceinline__ void insert(float s) { if (would_enter(s)) t.insert(s); }
 };
 
-template <int CODEC>
-struct UnionOps {
-    typedef BlockEnum<CODEC> E;
+constexpr uint32_t UNION_TILE = 512;            // docids per tile (accumulators: 2 KB per warp)
 
-    // freqs of the list's current block as plain values (freq - 1) in dst[0..size)
-    static __device__ DS2I_DECODE_INLINE void decode_freqs_plain(WarpCtx& c, DevIndex const& idx, ListState* s, uint32_t* dst) {
-        const unsigned lane = lane_id();
-        uint32_t off = stage_range(c, idx.lists, s->data_off + s->freqs_off, s->data_off + s->block_end);
-        bool prefix;
-        uint32_t size = s->cur_size;
-        uint32_t consumed = decode_values<CODEC>(c, off, size, 0xffffffffu, dst, prefix);
-        c.c_freqs_blocks += 1; c.c_freqs_bytes += consumed;
-        if (prefix) {
-            uint32_t d[4];
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-                uint32_t i = 32 * j + lane;
-                d[j] = (i < size) ? dst[i] - (i ? dst[i - 1] : 0u) : 0u;
-            }
-            __syncwarp();
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) dst[32 * j + lane] = d[j];
-            __syncwarp();
-        }
-    }
+// per query term: cursor + the decoded docids and freqs of the current block
+struct UnionList {
+    uint64_t data_off;      // absolute byte offset of the list's block data inside m_lists
+    uint32_t bfirst;        // the list's first entry in the block directory
+    uint32_t nblocks;
+    uint32_t n;
+    uint32_t last_max;      // last docid of the list
+    uint32_t pos;           // essential cursor: first unconsumed posting of the current block
+    uint32_t done;          // as an essential list: nothing left inside the item's docid range
+    // written together by lane 0 after every docs decode (one 16-B store)
+    uint32_t cur_block;     // 0xffffffff: not positioned yet
+    uint32_t cur_max;
+    uint32_t cur_end;
+    uint32_t freqs_off;
+    uint32_t docs[BLOCK];   // absolute docids of the current block (0xffffffff beyond its size)
+    uint32_t freqs[BLOCK];  // freqs - 1 of the current block (kept for essential lists only)
+};
+static_assert(sizeof(UnionList) == 48 + 8 * BLOCK, "UnionList layout");
 
-    static __device__ __forceinline__ uint32_t count_less(const ListState* s, uint32_t bound) {
-        uint4 v = reinterpret_cast<const uint4*>(s->docs)[lane_id()];
-        uint32_t cnt = (v.x < bound) + (v.y < bound) + (v.z < bound) + (v.w < bound);
-        return __reduce_add_sync(FULL, cnt);
-    }
-
-    // essential list: docs + freqs of block b, cursor at its first element
-    static __device__ __forceinline__ void load_essential_block(WarpCtx& c, DevIndex const& idx, ListState* s, BlockMeta const& bm) {
-        E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
-        const uint32_t b = bm.block;
-        if (b + 1 < s->nblocks) prefetch_l2(idx.lists + s->data_off + s->block_end + lane_id() * 32u);
-        decode_freqs_plain(c, idx, s, s->freqs);
-        if (lane_id() == 0) s->freqs_ready = 1;
-        __syncwarp();
-    }
+struct UnionWarp {
+    float qw[MAX_TERMS];
+    float ub[MAX_TERMS];
+    uint64_t bar;
+    uint64_t pad;
 };
 
-constexpr size_t UNION_MERGE_BYTES = 128 * 4 + 128 * 4 + 128 * 2;
-__host__ __device__ constexpr size_t union_warp_smem_bytes(int slots) { return warp_smem_bytes(slots) + UNION_MERGE_BYTES; }
+__host__ __device__ constexpr size_t union_warp_smem_bytes(int slots) {
+    return sizeof(UnionWarp) + size_t(slots) * sizeof(UnionList) + UNION_TILE * 4 /* accumulators */ + BLOCK * 4 /* freqs of a probed block */ +
+           STAGE_WORDS * 4 + SCRATCH_WORDS * 4;
+}
+
+__device__ __forceinline__ uint32_t union_block_size(const UnionList* s) {
+    const uint32_t n = s->n, b = s->cur_block;
+    return ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
+}
+
+// essential list: docs + plain freqs of block bm.block, cursor at its first element
+template <int CODEC>
+__device__ __forceinline__ void union_load_block(AndCtx& c, UnionList* s, uint32_t slot, BlockMeta const& bm) {
+    const unsigned lane = lane_id();
+    and_decode_docs<CODEC>(c, s, slot, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+    const bool prefix = and_decode_freqs<CODEC>(c, s, slot, smem_offset(s->freqs));
+    if (prefix) {       // interpolative leaves prefix sums
+        const uint32_t size = union_block_size(s);
+        uint32_t d[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t i = 32 * j + lane;
+            d[j] = (i < size) ? s->freqs[i] - (i ? s->freqs[i - 1] : 0u) : 0u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) s->freqs[32 * j + lane] = d[j];
+    }
+    if (lane == 0) s->pos = 0;
+    __syncwarp();
+}
 
 template <int CODEC>
-__global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, UnionJob job, uint32_t k, int slots) {
+__global__ void __launch_bounds__(128, 4) union_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, UnionJob job, uint32_t k, int slots) {
     s16_table_init(smem_words(0));
     __syncthreads();
 
-    typedef BlockEnum<CODEC> E;
-    typedef UnionOps<CODEC> U;
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    // per warp: [WarpSmem | slots x ListState | merge buffers | staging window | codec scratch]
+    // per warp: [UnionWarp | slots x UnionList | accumulators | freqs buffer | staging window | codec scratch]
     uint8_t* base = g_smem + S16_TAB_BYTES + warp * union_warp_smem_bytes(slots);
-    WarpSmem* ws = reinterpret_cast<WarpSmem*>(base);
-    ListState* st = reinterpret_cast<ListState*>(base + sizeof(WarpSmem));
-    uint32_t* cdoc = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState));   // merged candidate docids
-    uint32_t* ftmp = cdoc + 128;                                                                              // freqs of a probed block
-    uint16_t* cinfo = reinterpret_cast<uint16_t*>(ftmp + 128);                                                // (list << 8) | slot per candidate
-    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(WarpSmem) + size_t(slots) * sizeof(ListState) + UNION_MERGE_BYTES);
-    uint32_t* scratch = stage + STAGE_WORDS;
+    UnionWarp* ws = reinterpret_cast<UnionWarp*>(base);
+    UnionList* st = reinterpret_cast<UnionList*>(base + sizeof(UnionWarp));
+    float* acc = reinterpret_cast<float*>(base + sizeof(UnionWarp) + size_t(slots) * sizeof(UnionList));
+    uint32_t* ftmp = reinterpret_cast<uint32_t*>(acc + UNION_TILE);
+    uint32_t* stage = ftmp + BLOCK;
+    uint32_t* stack = stage + STAGE_WORDS;
 
-    WarpCtx c;
-    ctx_init(c, stage, scratch, &ws->bar, idx.codec);
+    AndCtx c;
+    c.lists = idx.lists; c.stage = stage; c.bar = &ws->bar;
+    c.stage_off = smem_offset(stage); c.stack_off = smem_offset(stack); c.ftmp_off = smem_offset(ftmp);
+    c.phase = 0; c.win_slot = 0xffffffffu; c.win_delta = 0;
+    c.c_docs_blocks = c.c_freqs_blocks = c.c_bytes_docs = c.c_bytes_freqs = c.c_maxs = c.c_scored = 0;
+    if (lane == 0) { mbar_init(c.bar, 1); fence_mbar_init(); }
+#pragma unroll
+    for (uint32_t p = 0; p < UNION_TILE / 128; ++p) reinterpret_cast<float4*>(acc)[32 * p + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
 
     while (true) {
         uint32_t ii = 0;
@@ -133,182 +152,145 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
         topk.init(k);
 
         // slots in increasing max_weight order (queries.hpp:521-524), upper bounds by sequential prefix sum (:526-530)
+        c.win_slot = 0xffffffffu;
         __syncwarp();
         if (lane < nt) {
-            uint32_t src = batch.ord_maxw[t0 + lane];
+            const uint32_t src = batch.ord_maxw[t0 + lane];
             ws->qw[lane] = batch.q_weight[t0 + src];
-            ws->mw[lane] = batch.max_weight[t0 + src];
-            ListDir d = idx.dir[batch.term[t0 + src]];
-            uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-            ListState* s = &st[lane];
-            s->maxs_off = d.maxs_off;
+            ws->ub[lane] = batch.max_weight[t0 + src];
+            const uint32_t term = batch.term[t0 + src];
+            const ListDir d = idx.dir[term];
+            const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+            const uint32_t bfirst = idx.bfirst[term];
+            UnionList* s = &st[lane];
             s->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
-            s->n = d.n; s->nblocks = nblocks; s->data_bytes = d.data_bytes;
-            s->cur_block = 0xffffffffu; s->cur_max = 0; s->prev_max = 0xffffffffu; s->cur_size = 0; s->pos = 0;
-            s->freqs_ready = 0; s->win_block = 0xffffffffu;
-            s->bfirst = idx.bfirst[batch.term[t0 + src]];
-            s->last_max = __ldg(idx.bdir + s->bfirst + nblocks - 1).x;
-            s->exhausted = s->last_max < lo ? 1u : 0u;
+            s->bfirst = bfirst; s->nblocks = nblocks; s->n = d.n;
+            s->last_max = __ldg(idx.bdir + bfirst + nblocks - 1).x;
+            s->pos = 0;
+            s->done = s->last_max < lo ? 1u : 0u;
+            s->cur_block = 0xffffffffu; s->cur_max = 0; s->cur_end = 0; s->freqs_off = 0;
         }
         __syncwarp();
         if (lane == 0) {
-            float acc = ws->mw[0];
-            ws->ub[0] = acc;
-            for (uint32_t i = 1; i < nt; ++i) { acc = acc + ws->mw[i]; ws->ub[i] = acc; }
+            float a = ws->ub[0];
+            for (uint32_t i = 1; i < nt; ++i) { a = a + ws->ub[i]; ws->ub[i] = a; }
         }
         __syncwarp();
 
-        uint32_t ne = 0;                 // lists [0, ne) are non-essential
-        uint32_t positioned = 0;         // bit i: list i has been positioned as an essential list
-        while (true) {
-            // refresh the shared floor, grow the non-essential prefix (queries.hpp:568-574)
-            {
-                uint32_t g = 0;
-                if (lane == 0) g = *reinterpret_cast<volatile uint32_t*>(job.query_threshold + q);
-                g = __shfl_sync(FULL, g, 0);
-                topk.floor_ = fmaxf(topk.floor_, __uint_as_float(g));
-            }
-            while (ne < nt && !topk.would_enter(ws->ub[ne])) ne += 1;
-            if (ne == nt) break;
+        // lists [0, ne) are non-essential (queries.hpp:568-574); the shared floor may already exclude some
+        uint32_t ne = 0;
+        {
+            uint32_t g = 0;
+            if (lane == 0) g = *reinterpret_cast<volatile uint32_t*>(job.query_threshold + q);
+            g = __shfl_sync(FULL, g, 0);
+            topk.floor_ = fmaxf(topk.floor_, __uint_as_float(g));
+        }
+        while (ne < nt && !topk.would_enter(ws->ub[ne])) ne += 1;
 
-            // essential lists that have not been opened yet: position them at the start of the range
+        // essential lists: position at the first posting >= lo
+        for (uint32_t e = ne; e < nt; ++e) {
+            UnionList* s = &st[e];
+            if (s->done) continue;
+            const BlockMeta bm = and_find_block(c.c_maxs, idx.bdir + s->bfirst, s->nblocks, 0u, 0xffffffffu, 0u, lo);
+            union_load_block<CODEC>(c, s, e, bm);
+            const uint4 v = reinterpret_cast<const uint4*>(s->docs)[lane];
+            const uint32_t p = __reduce_add_sync(FULL, (v.x < lo) + (v.y < lo) + (v.z < lo) + (v.w < lo));
+            if (lane == 0) s->pos = p;
+            __syncwarp();
+        }
+
+        while (ne < nt) {
+            // next tile: the one holding the smallest unconsumed essential posting
+            uint32_t nxt = 0xffffffffu;
             for (uint32_t e = ne; e < nt; ++e) {
-                if (positioned & (1u << e)) continue;
-                positioned |= 1u << e;
-                ListState* s = &st[e];
-                if (s->exhausted) continue;
-                uint32_t cb = s->cur_block;
-                if (cb == 0xffffffffu || s->cur_max < lo) {
-                    // never touched (or left behind as a probed list): find the block holding the first docid >= lo
-                    bool fresh = cb == 0xffffffffu;
-                    BlockMeta bm = and_find_block(c.c_maxs, idx.bdir + s->bfirst, s->nblocks, fresh ? 0u : cb + 1, fresh ? 0xffffffffu : s->cur_max,
-                                                  fresh ? 0u : s->block_end, lo);
-                    U::load_essential_block(c, idx, s, bm);
-                    uint32_t p = U::count_less(s, lo);
-                    if (lane == 0) s->pos = p;
-                    __syncwarp();
-                } else if (!s->freqs_ready) {
-                    // was a probed (non-essential-style) list positioned inside the range: keep its cursor
-                    U::decode_freqs_plain(c, idx, s, s->freqs);
-                    if (lane == 0) s->freqs_ready = 1;
-                    __syncwarp();
-                }
+                const UnionList* s = &st[e];
+                if (!s->done) nxt = min(nxt, s->docs[s->pos]);
             }
+            if (nxt >= hi) break;
+            const uint32_t tile = nxt & ~(UNION_TILE - 1u);
+            const uint32_t limit = min(tile + UNION_TILE, hi);
 
-            // window: everything up to the smallest current block_max of the live essential lists, shrunk until
-            // the essential postings inside it number at most 128 (one merged candidate batch per window)
-            uint32_t w_hi = 0xffffffffu;
-            bool any = false;
+            // essential contributions, one list at a time in increasing max_weight order
             for (uint32_t e = ne; e < nt; ++e) {
-                const ListState* s = &st[e];
-                if (s->exhausted) continue;
-                any = true;
-                w_hi = min(w_hi, s->cur_max);
-            }
-            if (!any) break;
-            if (w_hi >= hi) w_hi = hi - 1;
-            uint32_t total;
-            while (true) {
-                total = 0;
-                uint32_t best_cnt = 0, best_e = ne;
-                for (uint32_t e = ne; e < nt; ++e) {
-                    ListState* s = &st[e];
-                    uint32_t end_e = s->exhausted ? s->pos : U::count_less(s, w_hi + 1u);     // elements <= w_hi
-                    uint32_t cnt = end_e > s->pos ? end_e - s->pos : 0u;
-                    if (lane == 0) s->pad = s->pos + cnt;                                        // window end inside the block
-                    if (cnt > best_cnt) { best_cnt = cnt; best_e = e; }
-                    total += cnt;
-                }
-                __syncwarp();
-                if (total <= 128u) break;
-                uint32_t take = max(1u, best_cnt * 120u / total);
-                w_hi = st[best_e].docs[st[best_e].pos + take - 1u];
-            }
-
-            if (total) {
-                // merged, sorted candidate batch: rank of a posting = postings of the window that precede it
-                // (ties between lists broken by list order, so copies of one document sit next to each other
-                // in increasing max_weight order — the reference's summation order, queries.hpp:545-554)
-                for (uint32_t e = ne; e < nt; ++e) {
-                    const ListState* se = &st[e];
-                    const uint32_t pos_e = se->pos, end_e = se->pad;
-                    if (end_e <= pos_e) continue;
-                    uint4 cv = reinterpret_cast<const uint4*>(se->docs)[lane];
-                    const uint32_t x[4] = {cv.x, cv.y, cv.z, cv.w};
-                    uint32_t rank[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rank[j] = 4 * lane + j - pos_e;
-                    for (uint32_t e2 = ne; e2 < nt; ++e2) {
-                        if (e2 == e) continue;
-                        const ListState* s2 = &st[e2];
-                        const uint32_t pos2 = s2->pos, end2 = s2->pad;
-                        if (end2 <= pos2) continue;
-                        const uint32_t* d2 = s2->docs;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t slot = 4 * lane + j;
-                            if (slot >= pos_e && slot < end_e) {
-                                uint32_t lb = lower_bound128(d2, x[j]);
-                                rank[j] += lb - pos2;
-                                if (e2 < e && lb < end2 && d2[lb] == x[j]) rank[j] += 1u;
-                            }
-                        }
-                    }
+                UnionList* s = &st[e];
+                if (s->done) continue;
+                const float qwe = ws->qw[e];
+                while (true) {
+                    const uint32_t pos = s->pos;
+                    const uint4 dv = reinterpret_cast<const uint4*>(s->docs)[lane];
+                    const uint4 fv = reinterpret_cast<const uint4*>(s->freqs)[lane];
+                    const uint32_t d[4] = {dv.x, dv.y, dv.z, dv.w};
+                    const uint32_t f[4] = {fv.x, fv.y, fv.z, fv.w};
+                    uint32_t below = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        uint32_t slot = 4 * lane + j;
-                        if (slot >= pos_e && slot < end_e) { cdoc[rank[j] & 127u] = x[j]; cinfo[rank[j] & 127u] = uint16_t((e << 8) | slot); }
-                    }
-                }
-                __syncwarp();
-
-                // every lane owns 4 consecutive entries of the merged batch; an entry that repeats its
-                // predecessor's docid is a copy and is folded into the first one
-                uint32_t cand[4], alive = 0;
-                float score[4], nl[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t r = 4 * lane + j;
-                    cand[j] = r < total ? cdoc[r] : 0xffffffffu;
-                    score[j] = 0.f; nl[j] = 0.f;
-                    if (r < total && (r == 0 || cdoc[r - 1] != cand[j])) {
-                        alive |= 1u << j;
-                        nl[j] = __ldg(wand.norm_lens + cand[j]);
-                        for (uint32_t t = 0; t < nt - ne; ++t) {
-                            uint32_t r2 = r + t;
-                            if (r2 >= total || cdoc[r2] != cand[j]) break;
-                            uint32_t info = cinfo[r2];
-                            score[j] += ws->qw[info >> 8] * doc_term_weight(st[info >> 8].freqs[info & 127u] + 1u, nl[j]);
+                        const bool in = d[j] < limit;       // the 0xffffffff padding beyond the block's size never is
+                        below += in;
+                        if (in && 4 * lane + j >= pos) {
+                            const float nl = __ldg(wand.norm_lens + d[j]);
+                            acc[d[j] - tile] += qwe * doc_term_weight(f[j] + 1u, nl);
                         }
                     }
+                    const uint32_t npos = __reduce_add_sync(FULL, below);
+                    __syncwarp();
+                    if (npos < union_block_size(s)) {       // the rest of the block lies beyond the tile
+                        if (lane == 0) s->pos = npos;
+                        break;
+                    }
+                    const uint32_t nb = s->cur_block + 1;
+                    if (nb >= s->nblocks || s->cur_max + 1u >= hi) {
+                        if (lane == 0) s->done = 1;
+                        break;
+                    }
+                    const uint2 en = __ldg(idx.bdir + s->bfirst + nb);     // the next block's (block_max, end)
+                    union_load_block<CODEC>(c, s, e, BlockMeta{nb, s->cur_end, en.y, s->cur_max, en.x});
                 }
+                __syncwarp();
+            }
+
+            // candidates: the touched accumulators, 128 consecutive docids per pass
+#pragma unroll 1
+            for (uint32_t p = 0; p < UNION_TILE / 128; ++p) {
+                const float4 a = reinterpret_cast<const float4*>(acc)[32 * p + lane];
+                float score[4] = {a.x, a.y, a.z, a.w};
+                uint32_t alive = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) alive |= (score[j] > 0.f) << j;
+                if (!__any_sync(FULL, alive)) continue;
+                reinterpret_cast<float4*>(acc)[32 * p + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t cand[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cand[j] = (alive & (1u << j)) ? tile + 128 * p + 4 * lane + j : 0xffffffffu;
                 c.c_scored += __reduce_add_sync(FULL, __popc(alive));
 
                 // non-essential lists from the highest bound down (queries.hpp:557-566); candidates are sorted,
                 // so every list is probed in one forward pass
                 uint32_t probing = alive;
                 for (uint32_t i = ne; i-- > 0;) {
+                    const float ubi = ws->ub[i];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if ((probing & (1u << j)) && !topk.would_enter(score[j] + ws->ub[i])) probing &= ~(1u << j);
+                        if ((probing & (1u << j)) && !topk.would_enter(score[j] + ubi)) probing &= ~(1u << j);
                     if (!__any_sync(FULL, probing)) break;
-                    ListState* s = &st[i];
-                    if (s->exhausted) continue;
+                    UnionList* s = &st[i];
+                    if (s->last_max < lo) continue;
                     const uint2* bd = idx.bdir + s->bfirst;
+                    const uint32_t last_max = s->last_max;
+                    const float qwi = ws->qw[i];
                     uint32_t pending = probing;
                     while (true) {
                         uint32_t mine = 0xffffffffu;
 #pragma unroll
                         for (int j = 3; j >= 0; --j) if (pending & (1u << j)) mine = cand[j];
-                        uint32_t cmin = __reduce_min_sync(FULL, mine);
+                        const uint32_t cmin = __reduce_min_sync(FULL, mine);
                         if (cmin == 0xffffffffu) break;
-                        if (cmin > s->last_max) break;                 // nothing of list i at or beyond cmin
-                        uint32_t cur_block = s->cur_block;
+                        if (cmin > last_max) break;                 // nothing of list i at or beyond cmin
+                        const uint32_t cur_block = s->cur_block;
                         if (cur_block == 0xffffffffu || cmin > s->cur_max) {
-                            bool fresh = cur_block == 0xffffffffu;
-                            BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
-                                                          fresh ? 0u : s->block_end, cmin);
-                            E::decode_docs_block_meta(c, idx, s, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+                            const bool fresh = cur_block == 0xffffffffu;
+                            const BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
+                                                                fresh ? 0u : s->cur_end, cmin);
+                            and_decode_docs<CODEC>(c, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
                         }
                         const uint32_t cur_max = s->cur_max;
                         const uint32_t* d = s->docs;
@@ -323,10 +305,17 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                             }
                         }
                         if (__any_sync(FULL, hitmask)) {
-                            U::decode_freqs_plain(c, idx, s, ftmp);
+                            float nl[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) nl[j] = (hitmask & (1u << j)) ? __ldg(wand.norm_lens + cand[j]) : 0.f;
+                            const bool prefix = and_decode_freqs<CODEC>(c, s, i, c.ftmp_off);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                if (hitmask & (1u << j)) score[j] += ws->qw[i] * doc_term_weight(ftmp[pos[j]] + 1u, nl[j]);
+                                if (hitmask & (1u << j)) {
+                                    const uint32_t pp = pos[j];
+                                    const uint32_t fq = prefix ? ftmp[pp] - (pp ? ftmp[pp - 1] : 0u) : ftmp[pp];
+                                    score[j] += qwi * doc_term_weight(fq + 1u, nl[j]);
+                                }
                             __syncwarp();
                         }
                     }
@@ -337,37 +326,25 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
                 for (int j = 0; j < 4; ++j) {
                     unsigned want = __ballot_sync(FULL, (alive & (1u << j)) && topk.would_enter(score[j]));
                     while (want) {
-                        int src = __ffs(want) - 1;
+                        const int src = __ffs(want) - 1;
                         want &= want - 1;
-                        float sc = __shfl_sync(FULL, score[j], src);
-                        topk.insert(sc);
-                    }
-                }
-                __syncwarp();
-                if (lane >= ne && lane < nt) st[lane].pos = st[lane].pad;       // cursors move past the window
-                __syncwarp();
-            }
-
-            // publish the threshold, then move consumed essential lists to their next block
-            if (topk.t.size == topk.t.k && topk.t.thr > topk.floor_) {
-                if (lane == 0) atomicMax(job.query_threshold + q, __float_as_uint(topk.t.thr));
-            }
-            bool range_done = (w_hi + 1u >= hi);
-            for (uint32_t e = ne; e < nt; ++e) {
-                ListState* s = &st[e];
-                if (s->exhausted) continue;
-                if (range_done) { if (lane == 0) s->exhausted = 1; continue; }
-                if (s->pos >= s->cur_size) {
-                    uint32_t nb = s->cur_block + 1;
-                    if (nb >= s->nblocks || s->cur_max + 1u >= hi) { __syncwarp(); if (lane == 0) s->exhausted = 1; __syncwarp(); }
-                    else {
-                        const uint2 en = __ldg(idx.bdir + s->bfirst + nb);     // the next block's (block_max, end)
-                        U::load_essential_block(c, idx, s, BlockMeta{nb, s->block_end, en.y, s->cur_max, en.x});
+                        topk.insert(__shfl_sync(FULL, score[j], src));
                     }
                 }
             }
             __syncwarp();
-            if (range_done) break;
+
+            // publish the threshold, refresh the shared floor, grow the non-essential prefix
+            if (topk.t.size == topk.t.k && topk.t.thr > topk.floor_) {
+                if (lane == 0) atomicMax(job.query_threshold + q, __float_as_uint(topk.t.thr));
+            }
+            {
+                uint32_t g = 0;
+                if (lane == 0) g = *reinterpret_cast<volatile uint32_t*>(job.query_threshold + q);
+                g = __shfl_sync(FULL, g, 0);
+                topk.floor_ = fmaxf(topk.floor_, __uint_as_float(g));
+            }
+            while (ne < nt && !topk.would_enter(ws->ub[ne])) ne += 1;
         }
 
         if (lane == 0) job.item_sizes[ii] = topk.t.size;
@@ -377,8 +354,8 @@ __global__ void __launch_bounds__(128) union_block_kernel(DevIndex idx, DevWand 
     if (batch.stats && lane == 0) {
         atomicAdd(&batch.stats[0], (unsigned long long)c.c_docs_blocks);
         atomicAdd(&batch.stats[1], (unsigned long long)c.c_freqs_blocks);
-        atomicAdd(&batch.stats[2], (unsigned long long)c.c_docs_bytes);
-        atomicAdd(&batch.stats[3], (unsigned long long)c.c_freqs_bytes);
+        atomicAdd(&batch.stats[2], (unsigned long long)c.c_bytes_docs);
+        atomicAdd(&batch.stats[3], (unsigned long long)c.c_bytes_freqs);
         atomicAdd(&batch.stats[4], (unsigned long long)c.c_maxs);
         atomicAdd(&batch.stats[5], (unsigned long long)c.c_scored);
     }
