@@ -134,7 +134,8 @@ struct ds2i_gpu_batch {
     // block-parallel union path (wand / maxscore): work items = (query, docid range)
     dev_buf<UnionItem> un_items;
     dev_buf<uint32_t> un_order, un_item_begin, un_item_sizes, un_threshold;
-    dev_buf<float> un_item_scores;
+    dev_buf<float> un_item_scores, un_ub;
+    size_t un_item_scores_k = 0;      // k the partial top-k buffer was sized for
     uint32_t n_un_items = 0;
     unsigned items_built = 3;      // which work-item lists exist (bit 0 conjunctive, bit 1 union)
     uint64_t launches = 0;
@@ -400,29 +401,53 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
     CUDA_TRY(b->and_item_scores.alloc(items.size() * MAX_K));
 
-    // work items of the union path: heavy queries are cut into docid ranges
+    // work items of the union path: (query, driving list, run of its blocks), highest-weight lists first
     {
         std::vector<UnionItem> uitems;
         std::vector<uint32_t> ubegin(nq + 1, 0), uorder;
+        std::vector<float> ub(term.size(), 0.f);
         // postings per work item; DS2I_GPU_UNION_ITEM_POSTINGS overrides it (tests use a tiny value to
-        // exercise the range-splitting path on small collections)
-        uint64_t per_item = 131072;
+        // exercise the splitting path on small collections)
+        uint64_t per_item = 16384;
         if (const char* ev = getenv("DS2I_GPU_UNION_ITEM_POSTINGS")) per_item = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
-        for (size_t q = 0; q < nq; ++q) {
-            if ((which & 2u) && q_begin[q + 1] > q_begin[q]) {
-                uint64_t r = std::min<uint64_t>(64, std::max<uint64_t>(1, (cost[q] + per_item - 1) / per_item));
-                for (uint64_t i = 0; i < r; ++i) {
-                    uint64_t lo = ix->num_docs * i / r, hi = ix->num_docs * (i + 1) / r;
-                    if (hi > lo) uitems.push_back(UnionItem{uint32_t(q), uint32_t(lo), uint32_t(hi)});
+        const uint32_t item_blocks = uint32_t(std::min<uint64_t>(65535, std::max<uint64_t>(1, per_item / BLOCK)));
+        std::vector<uint32_t> level_count(MAX_TERMS + 1, 0);
+        for (size_t q = 0; q < nq && (which & 2u); ++q) {
+            const uint32_t t0 = q_begin[q], nt = q_begin[q + 1] - t0;
+            float acc = 0.f;
+            for (uint32_t i = 0; i < nt; ++i) {          // queries.hpp:526-530, same sequential fp32 sum
+                const float mw = max_weight[t0 + ord_maxw[t0 + i]];
+                acc = i ? acc + mw : mw;
+                ub[t0 + i] = acc;
+            }
+            for (uint32_t level = 0; level < nt; ++level) {
+                const uint32_t e = nt - 1 - level;
+                const uint64_t nb = (list_size_of(ix, term[t0 + ord_maxw[t0 + e]]) + BLOCK - 1) / BLOCK;
+                for (uint64_t fb = 0; fb < nb; fb += item_blocks) {
+                    uitems.push_back(UnionItem{uint32_t(q), uint32_t(fb), uint16_t(e), uint16_t(std::min<uint64_t>(item_blocks, nb - fb))});
+                    level_count[level] += 1;
                 }
             }
             ubegin[q + 1] = uint32_t(uitems.size());
         }
-        for (uint32_t qi : sched)
-            for (uint32_t it = ubegin[qi]; it < ubegin[qi + 1]; ++it) uorder.push_back(it);
+        if (!(which & 2u)) for (size_t q = 0; q < nq; ++q) ubegin[q + 1] = 0;
+        // processing order: level by level (level 0 = each query's highest-weight list), costliest queries first inside a level
+        {
+            std::vector<uint32_t> level_pos(MAX_TERMS + 1, 0);
+            for (int l = 1; l <= MAX_TERMS; ++l) level_pos[l] = level_pos[l - 1] + level_count[l - 1];
+            uorder.resize(uitems.size());
+            for (uint32_t qi : sched) {
+                const uint32_t nt = q_begin[qi + 1] - q_begin[qi];
+                for (uint32_t it = ubegin[qi]; it < ubegin[qi + 1]; ++it) {
+                    const uint32_t level = nt - 1 - uitems[it].slot;
+                    uorder[level_pos[level]++] = it;
+                }
+            }
+        }
         b->n_un_items = uint32_t(uitems.size());
         CUDA_TRY(b->un_items.upload(uitems)); CUDA_TRY(b->un_order.upload(uorder)); CUDA_TRY(b->un_item_begin.upload(ubegin));
-        CUDA_TRY(b->un_item_sizes.alloc(uitems.size())); CUDA_TRY(b->un_item_scores.alloc(uitems.size() * MAX_K));
+        CUDA_TRY(b->un_ub.upload(ub));
+        CUDA_TRY(b->un_item_sizes.alloc(uitems.size()));
         CUDA_TRY(b->un_threshold.alloc(nq));
     }
 
@@ -507,11 +532,13 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
     return fail(DS2I_E_UNSUPPORTED, "unknown codec");
 }
 
+constexpr int UNION_MIN_CTAS = 6;
+
 template <int CODEC>
 static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    auto kern = union_block_kernel<CODEC>;
+    auto kern = union_drive_kernel<CODEC, UNION_MIN_CTAS>;
     size_t smem = S16_TAB_BYTES + warps * union_warp_smem_bytes(b->max_terms);
     int per_sm = 0;
     int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
@@ -520,11 +547,14 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
     int grid = per_sm * ix->sm_count;
     int needed = int((b->n_un_items + warps - 1) / warps);
     if (grid > needed) grid = std::max(needed, 1);
+    if (b->un_item_scores_k < k || !b->un_item_scores.p) {      // partial top-k lists: k floats per item
+        CUDA_TRY(b->un_item_scores.alloc(size_t(b->n_un_items) * k));
+        b->un_item_scores_k = k;
+    }
     CUDA_TRY(cudaMemsetAsync(b->un_threshold.p, 0, std::max<size_t>(b->nq, 1) * sizeof(uint32_t)));
-    UnionJob job{b->un_items.p, b->un_order.p, b->n_un_items, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
+    UnionJob job{b->un_items.p, b->un_order.p, b->un_ub.p, b->n_un_items, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
     if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, b->wand->dev, db, job, k, b->max_terms); b->launches += 1; }
-    merge_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_sizes.p, b->un_item_scores.p,
-                                                 k, true, b->out_counts.p, b->out_scores.p);
+    merge_union_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_scores.p, k, b->out_counts.p, b->out_scores.p);
     return DS2I_OK;
 }
 
