@@ -187,7 +187,7 @@ class QueryBatch:
     def stats(self):
         s = np.zeros(8, dtype=np.uint64)
         _native.check(_native.lib().ds2i_gpu_batch_stats(self._h, _p(s, C.c_uint64)))
-        keys = ("docs_blocks", "freqs_blocks", "docs_bytes", "freqs_bytes", "block_maxs_read", "docs_scored", "launches")
+        keys = ("docs_blocks", "freqs_blocks", "docs_bytes", "freqs_bytes", "block_maxs_read", "docs_scored", "launches", "aux")
         return {k: int(v) for k, v in zip(keys, s)}
 
     def close(self):

@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
     deps = _sources((".cu", ".cuh", ".hpp", ".h", ".cpp"))
     nvcc = os.environ.get("NVCC", "nvcc")
     if force or _newer(LIB, deps):
-        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB, os.path.join(CSRC, "ds2i_gpu.cu")]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DS2I_NVCC_EXTRA", "").split() + ["-shared", "-o", LIB, os.path.join(CSRC, "ds2i_gpu.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         out = _run(cmd)

@@ -132,11 +132,10 @@ struct ds2i_gpu_batch {
     dev_buf<float> and_item_scores;
     uint32_t n_and_items = 0, and_chunk = AND_CHUNK_BLOCKS;
     // block-parallel union path (wand / maxscore): work items = (query, docid range)
-    dev_buf<UnionItem> un_items;
-    dev_buf<uint32_t> un_order, un_item_begin, un_item_sizes, un_threshold;
+    dev_buf<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_item_begin, un_item_sizes, un_threshold;
     dev_buf<float> un_item_scores, un_ub;
     size_t un_item_scores_k = 0;      // k the partial top-k buffer was sized for
-    uint32_t n_un_items = 0;
+    uint32_t n_un_items = 0, n_un_groups = 0, un_item_blocks = 64;
     unsigned items_built = 3;      // which work-item lists exist (bit 0 conjunctive, bit 1 union)
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -401,53 +400,57 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
     CUDA_TRY(b->and_item_scores.alloc(items.size() * MAX_K));
 
-    // work items of the union path: (query, driving list, run of its blocks), highest-weight lists first
+    // work items of the union path: (query, driving list, run of its blocks), highest-weight lists first.  Only the
+    // groups (one per query term) are materialised; the kernel derives the items from the prefix array.
     {
-        std::vector<UnionItem> uitems;
-        std::vector<uint32_t> ubegin(nq + 1, 0), uorder;
-        std::vector<float> ub(term.size(), 0.f);
+        const size_t nterms_total = term.size();
+        std::vector<float> ub(nterms_total, 0.f);
+        std::vector<uint32_t> ubegin(nq + 1, 0), gbase(nterms_total, 0), gchunks(nterms_total, 0);
         // postings per work item; DS2I_GPU_UNION_ITEM_POSTINGS overrides it (tests use a tiny value to
         // exercise the splitting path on small collections)
-        uint64_t per_item = 16384;
+        uint64_t per_item = 8192;
         if (const char* ev = getenv("DS2I_GPU_UNION_ITEM_POSTINGS")) per_item = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
-        const uint32_t item_blocks = uint32_t(std::min<uint64_t>(65535, std::max<uint64_t>(1, per_item / BLOCK)));
+        const uint32_t item_blocks = uint32_t(std::min<uint64_t>(1u << 20, std::max<uint64_t>(1, per_item / BLOCK)));
+        b->un_item_blocks = item_blocks;
         std::vector<uint32_t> level_count(MAX_TERMS + 1, 0);
+        uint64_t nitems = 0;
         for (size_t q = 0; q < nq && (which & 2u); ++q) {
             const uint32_t t0 = q_begin[q], nt = q_begin[q + 1] - t0;
             float acc = 0.f;
-            for (uint32_t i = 0; i < nt; ++i) {          // queries.hpp:526-530, same sequential fp32 sum
+            for (uint32_t i = 0; i < nt; ++i) {          // queries.hpp:526-530, same sequential fp32 sum; slot i = i-th list by max_weight
                 const float mw = max_weight[t0 + ord_maxw[t0 + i]];
                 acc = i ? acc + mw : mw;
                 ub[t0 + i] = acc;
+                const uint64_t nb = (list_size_of(ix, term[t0 + ord_maxw[t0 + i]]) + BLOCK - 1) / BLOCK;
+                gchunks[t0 + i] = uint32_t((nb + item_blocks - 1) / item_blocks);
+                gbase[t0 + i] = uint32_t(nitems);
+                nitems += gchunks[t0 + i];
+                level_count[nt - 1 - i] += 1;
             }
-            for (uint32_t level = 0; level < nt; ++level) {
-                const uint32_t e = nt - 1 - level;
-                const uint64_t nb = (list_size_of(ix, term[t0 + ord_maxw[t0 + e]]) + BLOCK - 1) / BLOCK;
-                for (uint64_t fb = 0; fb < nb; fb += item_blocks) {
-                    uitems.push_back(UnionItem{uint32_t(q), uint32_t(fb), uint16_t(e), uint16_t(std::min<uint64_t>(item_blocks, nb - fb))});
-                    level_count[level] += 1;
-                }
-            }
-            ubegin[q + 1] = uint32_t(uitems.size());
+            if (nitems > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many work items in one batch");
+            ubegin[q + 1] = uint32_t(nitems);
         }
-        if (!(which & 2u)) for (size_t q = 0; q < nq; ++q) ubegin[q + 1] = 0;
         // processing order: level by level (level 0 = each query's highest-weight list), costliest queries first inside a level
+        const size_t ngroups = (which & 2u) ? nterms_total : 0;
+        std::vector<uint32_t> gterm(ngroups), gquery(ngroups), gres(ngroups), gstart(ngroups + 1, 0);
         {
             std::vector<uint32_t> level_pos(MAX_TERMS + 1, 0);
             for (int l = 1; l <= MAX_TERMS; ++l) level_pos[l] = level_pos[l - 1] + level_count[l - 1];
-            uorder.resize(uitems.size());
             for (uint32_t qi : sched) {
-                const uint32_t nt = q_begin[qi + 1] - q_begin[qi];
-                for (uint32_t it = ubegin[qi]; it < ubegin[qi + 1]; ++it) {
-                    const uint32_t level = nt - 1 - uitems[it].slot;
-                    uorder[level_pos[level]++] = it;
+                if (!ngroups) break;
+                const uint32_t t0 = q_begin[qi], nt = q_begin[qi + 1] - t0;
+                for (uint32_t i = 0; i < nt; ++i) {
+                    const uint32_t pos = level_pos[nt - 1 - i]++;
+                    gterm[pos] = t0 + i; gquery[pos] = qi; gres[pos] = gbase[t0 + i]; gstart[pos + 1] = gchunks[t0 + i];
                 }
             }
+            for (size_t g = 0; g < ngroups; ++g) gstart[g + 1] += gstart[g];
         }
-        b->n_un_items = uint32_t(uitems.size());
-        CUDA_TRY(b->un_items.upload(uitems)); CUDA_TRY(b->un_order.upload(uorder)); CUDA_TRY(b->un_item_begin.upload(ubegin));
+        b->n_un_items = uint32_t(nitems); b->n_un_groups = uint32_t(ngroups);
+        CUDA_TRY(b->un_gstart.upload(gstart)); CUDA_TRY(b->un_gterm.upload(gterm)); CUDA_TRY(b->un_gquery.upload(gquery));
+        CUDA_TRY(b->un_gbase.upload(gres)); CUDA_TRY(b->un_item_begin.upload(ubegin));
         CUDA_TRY(b->un_ub.upload(ub));
-        CUDA_TRY(b->un_item_sizes.alloc(uitems.size()));
+        CUDA_TRY(b->un_item_sizes.alloc(nitems));
         CUDA_TRY(b->un_threshold.alloc(nq));
     }
 
@@ -532,7 +535,10 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
     return fail(DS2I_E_UNSUPPORTED, "unknown codec");
 }
 
-constexpr int UNION_MIN_CTAS = 6;
+#ifndef DS2I_UNION_MIN_CTAS
+#define DS2I_UNION_MIN_CTAS 6
+#endif
+constexpr int UNION_MIN_CTAS = DS2I_UNION_MIN_CTAS;
 
 template <int CODEC>
 static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
@@ -552,7 +558,7 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
         b->un_item_scores_k = k;
     }
     CUDA_TRY(cudaMemsetAsync(b->un_threshold.p, 0, std::max<size_t>(b->nq, 1) * sizeof(uint32_t)));
-    UnionJob job{b->un_items.p, b->un_order.p, b->un_ub.p, b->n_un_items, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
+    UnionJob job{b->un_gstart.p, b->un_gterm.p, b->un_gquery.p, b->un_gbase.p, b->un_ub.p, b->n_un_groups, b->n_un_items, b->un_item_blocks, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
     if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, b->wand->dev, db, job, k, b->max_terms); b->launches += 1; }
     merge_union_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_scores.p, k, b->out_counts.p, b->out_scores.p);
     return DS2I_OK;

@@ -31,19 +31,38 @@
 
 namespace ds2i_gpu {
 
-struct UnionItem { uint32_t query, first_block; uint16_t slot, nblocks; };      // slot: position in max_weight order
-static_assert(sizeof(UnionItem) == 12, "UnionItem layout");
-
+// Work items are implicit: group g = (query, list slot) owns ceil(nblocks / item_blocks) consecutive items.  Groups are
+// laid out in processing order; a warp maps a global item number to its group with a 32-ary search of the prefix
+// array, so the host prepares O(query terms) words instead of one record per item.
 struct UnionJob {
-    const UnionItem* items;      // in query order (item_begin[q] .. item_begin[q+1])
-    const uint32_t* order;       // processing order
+    const uint32_t* gstart;      // ngroups+1: items before group g, in processing order
+    const uint32_t* gterm;       // ngroups: index of the group's term in the batch's per-term arrays (max_weight order slot = gslot)
+    const uint32_t* gquery;      // ngroups
+    const uint32_t* gbase;       // ngroups: first result slot of the group (results are laid out in query order)
     const float* ub;             // per query term, in max_weight order: the reference's upper_bounds[] (queries.hpp:526-530)
-    uint32_t nitems;
+    uint32_t ngroups, nitems, item_blocks;
     uint32_t* work_counter;
     uint32_t* query_threshold;   // nq: float bits of the best published k-th score of the query
     uint32_t* item_sizes;
     float* item_scores;          // nitems * k
 };
+
+// last position p in [0, n) with a[p] <= x (a is non-decreasing, a[0] <= x): 32 probes per step
+__device__ __forceinline__ uint32_t warp_upper_group(const uint32_t* a, uint32_t n, uint32_t x) {
+    const unsigned lane = lane_id();
+    uint32_t lo = 0, hi = n;            // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint32_t span = hi - lo;
+        const uint32_t step = (span + 31u) / 32u;
+        const uint32_t p = lo + lane * step;
+        const bool le = p < hi && __ldg(a + p) <= x;
+        const unsigned m = __ballot_sync(FULL, le);          // lane 0 always set
+        const uint32_t f = 31u - __clz(m);
+        lo = lo + f * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
+}
 
 // top-k with a floor shared across the items of a query
 struct TopKShared {
@@ -66,11 +85,11 @@ __host__ __device__ constexpr size_t union_warp_smem_bytes(int slots) {
     return sizeof(UnionWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + STAGE_WORDS * 4 + SCRATCH_WORDS * 4;
 }
 
-// Look the pending candidates up in list s (slot i).  SCORE: hits add the list's BM25 term; otherwise hits are
-// cleared from `alive` (the document is owned by list i).  Candidates are sorted, the list cursor only moves forward.
-template <int CODEC, bool SCORE>
+// Look the candidates in `alive` up in list s (slot i).  score_mode: hits add the list's BM25 term; otherwise hits
+// are cleared from `alive` (the document is owned by list i).  Candidates are sorted, the list cursor only moves forward.
+template <int CODEC>
 __device__ __forceinline__ void union_probe(AndCtx& c, DevIndex const& idx, AndList* s, uint32_t i, const uint32_t (&cand)[4], uint32_t& alive,
-                                            uint32_t drv_max, bool sparse, float qwi, const float (&norm_len)[4], float (&score)[4], const uint32_t* ftmp) {
+                                            bool score_mode, float qwi, const float (&norm_len)[4], float (&score)[4], const uint32_t* ftmp) {
     const unsigned lane = lane_id();
     const uint2* bd = idx.bdir + s->bfirst;
     const uint32_t last_max = s->last_max;
@@ -91,43 +110,48 @@ __device__ __forceinline__ void union_probe(AndCtx& c, DevIndex const& idx, AndL
         }
         const uint32_t cur_max = s->cur_max;
         const uint32_t* d = s->docs;
-        if (sparse) {
-            // list i is sparser than the driver: usually none of its docids falls inside [cmin, drv_max], which
-            // one 16-B load and a ballot establish for all pending candidates at once
-            const uint4 v = reinterpret_cast<const uint4*>(d)[lane];
-            const bool in = (v.x >= cmin && v.x <= drv_max) || (v.y >= cmin && v.y <= drv_max) || (v.z >= cmin && v.z <= drv_max) ||
-                            (v.w >= cmin && v.w <= drv_max);
-            if (!__any_sync(FULL, in)) {
+        // the candidates this block answers
+        uint32_t inb = 0, top = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (cand[j] <= cur_max) pending &= ~(1u << j);
-                continue;
-            }
-        }
-        uint32_t hitmask = 0, pos[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            pos[j] = 0;
-            if ((pending & (1u << j)) && cand[j] <= cur_max) {
-                pos[j] = lower_bound128(d, cand[j]);
-                if (d[pos[j]] == cand[j]) hitmask |= 1u << j;
-                pending &= ~(1u << j);
-            }
-        }
-        if (SCORE) {
-            if (__any_sync(FULL, hitmask)) {
-                const bool prefix = and_decode_freqs<CODEC>(c, s, i, c.ftmp_off);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (hitmask & (1u << j)) {
-                        const uint32_t p = pos[j];
-                        const uint32_t f = prefix ? ftmp[p] - (p ? ftmp[p - 1] : 0u) : ftmp[p];
-                        score[j] += qwi * doc_term_weight(f + 1u, norm_len[j]);
-                    }
-                __syncwarp();
+        for (int j = 0; j < 4; ++j)
+            if ((pending & (1u << j)) && cand[j] <= cur_max) { inb |= 1u << j; top = cand[j]; }
+        pending &= ~inb;
+        const uint32_t nin = __reduce_add_sync(FULL, __popc(inb));
+        const uint4 v = reinterpret_cast<const uint4*>(d)[lane];
+        uint32_t hitmask = 0, pos[4] = {0, 0, 0, 0};
+        if (nin == 1) {
+            // a sparse list probing a dense one: one candidate per block, found by comparing it with all 128 docids at once
+            const uint32_t eq = (v.x == cmin ? 1u : 0u) | (v.y == cmin ? 2u : 0u) | (v.z == cmin ? 4u : 0u) | (v.w == cmin ? 8u : 0u);
+            const unsigned hb = __ballot_sync(FULL, eq != 0u);
+            if (hb) {
+                const uint32_t hl = __ffs(hb) - 1;
+                const uint32_t p = 4u * hl + __shfl_sync(FULL, uint32_t(__ffs(eq)) - 1u, hl);
+                hitmask = inb;
+                pos[0] = pos[1] = pos[2] = pos[3] = p;
             }
         } else {
-            alive &= ~hitmask;
+            // a dense list probing a sparse one: usually none of the block's docids falls inside the candidates' range
+            const uint32_t chi = __reduce_max_sync(FULL, top);
+            const bool in = (v.x >= cmin && v.x <= chi) || (v.y >= cmin && v.y <= chi) || (v.z >= cmin && v.z <= chi) || (v.w >= cmin && v.w <= chi);
+            if (!__any_sync(FULL, in)) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (inb & (1u << j)) {
+                    pos[j] = lower_bound128(d, cand[j]);
+                    if (d[pos[j]] == cand[j]) hitmask |= 1u << j;
+                }
+        }
+        if (!score_mode) alive &= ~hitmask;
+        else if (__any_sync(FULL, hitmask)) {
+            const bool prefix = and_decode_freqs<CODEC>(c, s, i, c.ftmp_off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (hitmask & (1u << j)) {
+                    const uint32_t p = pos[j];
+                    const uint32_t f = prefix ? ftmp[p] - (p ? ftmp[p - 1] : 0u) : ftmp[p];
+                    score[j] += qwi * doc_term_weight(f + 1u, norm_len[j]);
+                }
+            __syncwarp();
         }
     }
 }
@@ -160,11 +184,14 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
         if (lane == 0) ii = atomicAdd(job.work_counter, 1u);
         ii = __shfl_sync(FULL, ii, 0);
         if (ii >= job.nitems) break;
-        ii = job.order[ii];
-        const UnionItem item = job.items[ii];
-        const uint32_t q = item.query, e = item.slot;
+        const uint32_t g = warp_upper_group(job.gstart, job.ngroups, ii);
+        const uint32_t chunk = ii - __ldg(job.gstart + g);
+        const uint32_t q = __ldg(job.gquery + g);
+        const uint32_t first_block = chunk * job.item_blocks;
+        const uint32_t rslot = __ldg(job.gbase + g) + chunk;       // where this item's partial top-k goes
         const uint32_t t0 = batch.q_begin[q];
         const uint32_t nt = batch.q_begin[q + 1] - t0;
+        const uint32_t e = __ldg(job.gterm + g) - t0;
         const volatile uint32_t* thr_g = job.query_threshold + q;
 
         TopKShared topk;
@@ -172,7 +199,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
         topk.floor_ = __uint_as_float(*thr_g);
         const float ub_e = __ldg(job.ub + t0 + e) * INFLATE;
         if (!(ub_e > topk.floor_)) {           // list e is non-essential already: nothing it owns can enter
-            if (lane == 0) job.item_sizes[ii] = 0;
+            if (lane == 0) job.item_sizes[rslot] = 0;
             continue;
         }
 
@@ -198,12 +225,11 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
 
         AndList* sd = &st[e];
         const uint2* bd0 = idx.bdir + sd->bfirst;
-        const uint32_t n_e = sd->n;
         const float qw_e = ws->qw[e];
-        const uint32_t b_end = min(sd->nblocks, item.first_block + uint32_t(item.nblocks));
+        const uint32_t b_end = min(sd->nblocks, first_block + job.item_blocks);
         float published = topk.floor_;
         bool stop = false;
-        for (uint32_t c0 = item.first_block; c0 < b_end && !stop; c0 += 32) {
+        for (uint32_t c0 = first_block; c0 < b_end && !stop; c0 += 32) {
             const uint32_t c1 = min(b_end, c0 + 32u);
             // directory entries of 32 blocks of the driving list, one block per lane, in one round trip
             uint32_t m_max = 0, m_end = 0, first_prev_max = 0xffffffffu, first_prev_end = 0;
@@ -224,48 +250,42 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                 }
                 const uint4 cv = reinterpret_cast<const uint4*>(sd->docs)[lane];
                 const uint32_t cand[4] = {cv.x, cv.y, cv.z, cv.w};
-                const uint32_t drv_max = sd->cur_max;
                 uint32_t alive = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) alive |= (cand[j] != 0xffffffffu) << j;
                 float norm_len[4] = {0.f, 0.f, 0.f, 0.f}, score[4] = {0.f, 0.f, 0.f, 0.f};
 
-                // lists above e own every document they share with e
-                for (uint32_t i = nt - 1; i > e; --i) {
-                    AndList* s = &st[i];
-                    union_probe<CODEC, false>(c, idx, s, i, cand, alive, drv_max, s->n < n_e, 0.f, norm_len, score, ftmp);
-                    if (!__any_sync(FULL, alive)) break;
-                }
-                if (!__any_sync(FULL, alive)) continue;
-
-                // the survivors' own term: freqs of the driving block, norm_len gather
+                // every list from the highest bound down.  Lists above e own the documents they share with e (a hit
+                // drops the candidate); at e the survivors get their own term; lists below e complete the score
+                // while score + ub[i] can still enter (queries.hpp:557-566)
+                for (uint32_t i = nt; i-- > 0;) {
+                    if (i == e) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (alive & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
-                {
-                    const bool prefix = and_decode_freqs<CODEC>(c, sd, e, c.ftmp_off);
-                    const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
-                    uint32_t f0[4] = {fv.x, fv.y, fv.z, fv.w};
-                    if (prefix) {
-                        const uint32_t prev = lane ? ftmp[4 * lane - 1] : 0u;
-                        f0[3] -= f0[2]; f0[2] -= f0[1]; f0[1] -= f0[0]; f0[0] -= prev;
+                        for (int j = 0; j < 4; ++j)
+                            if (alive & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
+                        const bool prefix = and_decode_freqs<CODEC>(c, sd, e, c.ftmp_off);
+                        const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
+                        uint32_t f0[4] = {fv.x, fv.y, fv.z, fv.w};
+                        if (prefix) {
+                            const uint32_t prev = lane ? ftmp[4 * lane - 1] : 0u;
+                            f0[3] -= f0[2]; f0[2] -= f0[1]; f0[1] -= f0[0]; f0[0] -= prev;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (alive & (1u << j)) score[j] = qw_e * doc_term_weight(f0[j] + 1u, norm_len[j]);
+                        c.c_scored += __reduce_add_sync(FULL, __popc(alive));
+                        continue;
                     }
-                    __syncwarp();
+                    if (i < e) {
+                        const float bar = topk.bar(), ubi = ws->ub[i];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (alive & (1u << j)) score[j] = qw_e * doc_term_weight(f0[j] + 1u, norm_len[j]);
-                }
-                c.c_scored += __reduce_add_sync(FULL, __popc(alive));
-
-                // lists below e from the highest bound down (queries.hpp:557-566)
-                for (uint32_t i = e; i-- > 0;) {
-                    const float bar = topk.bar(), ubi = ws->ub[i];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if ((alive & (1u << j)) && !(score[j] + ubi > bar)) alive &= ~(1u << j);
-                    if (!__any_sync(FULL, alive)) break;
-                    AndList* s = &st[i];
-                    union_probe<CODEC, true>(c, idx, s, i, cand, alive, drv_max, s->n < n_e, ws->qw[i], norm_len, score, ftmp);
+                        for (int j = 0; j < 4; ++j)
+                            if ((alive & (1u << j)) && !(score[j] + ubi > bar)) alive &= ~(1u << j);
+                        if (!__any_sync(FULL, alive)) break;
+                    }
+                    union_probe<CODEC>(c, idx, &st[i], i, cand, alive, i < e, ws->qw[i], norm_len, score, ftmp);
+                    if (i > e && !__any_sync(FULL, alive)) break;
                 }
 
                 // heap: only scores that can still enter
@@ -285,8 +305,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
             }
         }
 
-        if (lane == 0) job.item_sizes[ii] = topk.t.size;
-        if (lane < topk.t.size) job.item_scores[size_t(ii) * k + lane] = topk.t.v;
+        if (lane == 0) job.item_sizes[rslot] = topk.t.size;
+        if (lane < topk.t.size) job.item_scores[size_t(rslot) * k + lane] = topk.t.v;
     }
 
     if (batch.stats && lane == 0) {
