@@ -22,11 +22,11 @@ namespace ds2i_gpu {
 
 constexpr uint32_t AND_CHUNK_BLOCKS = 32;     // blocks of the shortest list per work item
 
-struct AndItem { uint32_t query, first_block; };
-
+// Work items are implicit: query sched[p] owns ceil(blocks of its shortest list / chunk_blocks) consecutive items; a warp
+// maps a global item number to its query with a 32-ary search of the prefix array gstart (in processing order).
 struct AndJob {
-    const AndItem* items;      // in query order (item_begin[q] .. item_begin[q+1])
-    const uint32_t* order;     // processing order: items of the costliest queries first
+    const uint32_t* gstart;      // nq+1: items before the p-th query of the processing order
+    const uint32_t* item_begin;  // nq+1: first result slot of query q (results are laid out in query order)
     uint32_t nitems;
     uint32_t chunk_blocks;     // blocks of the shortest list per item (<= 32)
     uint32_t* work_counter;
@@ -34,6 +34,23 @@ struct AndJob {
     uint32_t* item_sizes;      // nitems: entries in the item's partial top-k
     float* item_scores;        // nitems * k
 };
+
+// last position p in [0, n) with a[p] <= x (a is non-decreasing, a[0] <= x): 32 probes per step
+__device__ __forceinline__ uint32_t warp_upper_group(const uint32_t* a, uint32_t n, uint32_t x) {
+    const unsigned lane = lane_id();
+    uint32_t lo = 0, hi = n;            // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint32_t span = hi - lo;
+        const uint32_t step = (span + 31u) / 32u;
+        const uint32_t p = lo + lane * step;
+        const bool le = p < hi && __ldg(a + p) <= x;
+        const unsigned m = __ballot_sync(FULL, le);          // lane 0 always set
+        const uint32_t f = 31u - __clz(m);
+        lo = lo + f * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
+}
 
 // per query term: cursor + the decoded docids of the current block
 struct AndList {
@@ -242,9 +259,11 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         if (lane == 0) ii = atomicAdd(job.work_counter, 1u);
         ii = __shfl_sync(FULL, ii, 0);
         if (ii >= job.nitems) break;
-        ii = job.order[ii];
-        const AndItem item = job.items[ii];
-        const uint32_t q = item.query;
+        const uint32_t gpos = warp_upper_group(job.gstart, batch.nq, ii);
+        const uint32_t q = batch.sched[gpos];
+        const uint32_t chunk = ii - __ldg(job.gstart + gpos);
+        const uint32_t first_block = chunk * job.chunk_blocks;
+        ii = __ldg(job.item_begin + q) + chunk;      // result slot
         const uint32_t t0 = batch.q_begin[q];
         const uint32_t nt = batch.q_begin[q + 1] - t0;
         uint32_t matches = 0;
@@ -271,23 +290,23 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         __syncwarp();
 
         const uint32_t nb0 = st[0].nblocks;
-        const uint32_t b_end = min(nb0, item.first_block + job.chunk_blocks);
+        const uint32_t b_end = min(nb0, first_block + job.chunk_blocks);
         // directory entries of the whole chunk of the driving list, one block per lane, in one round trip
         uint32_t m_max = 0, m_end = 0, first_prev_max = 0xffffffffu, first_prev_end = 0;
         {
             static_assert(AND_CHUNK_BLOCKS <= 32, "one lane per block of the chunk");
             const uint2* bd0 = idx.bdir + st[0].bfirst;
-            const uint32_t bi = item.first_block + lane;
+            const uint32_t bi = first_block + lane;
             if (bi < b_end) { const uint2 en = __ldg(bd0 + bi); m_max = en.x; m_end = en.y; }
-            if (item.first_block) {
-                const uint2 en = __ldg(bd0 + item.first_block - 1);
+            if (first_block) {
+                const uint2 en = __ldg(bd0 + first_block - 1);
                 first_prev_max = en.x; first_prev_end = en.y;
             }
         }
         bool exhausted = false;
-        for (uint32_t b0 = item.first_block; b0 < b_end && !exhausted; ++b0) {
+        for (uint32_t b0 = first_block; b0 < b_end && !exhausted; ++b0) {
             {
-                const uint32_t l = b0 - item.first_block;
+                const uint32_t l = b0 - first_block;
                 const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
                 and_decode_docs<CODEC>(c, &st[0], 0u, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
                                        __shfl_sync(FULL, m_max, l));

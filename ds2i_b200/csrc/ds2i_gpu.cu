@@ -127,9 +127,9 @@ struct ds2i_gpu_batch {
     dev_buf<uint64_t> out_counts;
     dev_buf<unsigned long long> stats;
     // block-at-a-time conjunctive path: work items = (query, chunk of blocks of its shortest list)
-    dev_buf<AndItem> and_items;
-    dev_buf<uint32_t> and_order, and_item_begin, and_item_counts, and_item_sizes;
+    dev_buf<uint32_t> and_gstart, and_item_begin, and_item_counts, and_item_sizes;
     dev_buf<float> and_item_scores;
+    size_t and_item_scores_k = 0;
     uint32_t n_and_items = 0, and_chunk = AND_CHUNK_BLOCKS;
     // block-parallel union path (wand / maxscore): work items = (query, docid range)
     dev_buf<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_item_begin, un_item_sizes, un_threshold;
@@ -384,21 +384,20 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     uint32_t and_chunk = AND_CHUNK_BLOCKS;
     if (const char* ev = getenv("DS2I_GPU_AND_CHUNK_BLOCKS")) and_chunk = std::min<uint32_t>(32, std::max<uint32_t>(1, uint32_t(atoi(ev))));
     b->and_chunk = and_chunk;
-    std::vector<AndItem> items;
-    std::vector<uint32_t> item_begin(nq + 1, 0), item_order;
-    for (size_t q = 0; q < nq && (which & 1u); ++q) {
-        uint64_t nb0 = (shortest[q] + BLOCK - 1) / BLOCK;
-        for (uint64_t fb = 0; fb < nb0; fb += and_chunk) items.push_back(AndItem{uint32_t(q), uint32_t(fb)});
-        item_begin[q + 1] = uint32_t(items.size());
+    std::vector<uint32_t> item_begin(nq + 1, 0), and_gstart(nq + 1, 0);
+    {
+        uint64_t nitems = 0;
+        for (size_t q = 0; q < nq && (which & 1u); ++q) {
+            nitems += ((shortest[q] + BLOCK - 1) / BLOCK + and_chunk - 1) / and_chunk;
+            if (nitems > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many work items in one batch");
+            item_begin[q + 1] = uint32_t(nitems);
+        }
+        // the items of the costliest queries come first
+        for (size_t p = 0; p < nq; ++p) and_gstart[p + 1] = and_gstart[p] + (item_begin[sched[p] + 1] - item_begin[sched[p]]);
+        b->n_and_items = uint32_t(nitems);
     }
-    // the items of the costliest queries come first
-    item_order.reserve(items.size());
-    for (uint32_t qi : sched)
-        for (uint32_t it = item_begin[qi]; it < item_begin[qi + 1]; ++it) item_order.push_back(it);
-    b->n_and_items = uint32_t(items.size());
-    CUDA_TRY(b->and_items.upload(items)); CUDA_TRY(b->and_order.upload(item_order)); CUDA_TRY(b->and_item_begin.upload(item_begin));
-    CUDA_TRY(b->and_item_counts.alloc(items.size())); CUDA_TRY(b->and_item_sizes.alloc(items.size()));
-    CUDA_TRY(b->and_item_scores.alloc(items.size() * MAX_K));
+    CUDA_TRY(b->and_gstart.upload(and_gstart)); CUDA_TRY(b->and_item_begin.upload(item_begin));
+    CUDA_TRY(b->and_item_counts.alloc(b->n_and_items)); CUDA_TRY(b->and_item_sizes.alloc(b->n_and_items));
 
     // work items of the union path: (query, driving list, run of its blocks), highest-weight lists first.  Only the
     // groups (one per query term) are materialised; the kernel derives the items from the prefix array.
@@ -507,7 +506,11 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
         int grid = per_sm * ix->sm_count;
         int needed = int((b->n_and_items + warps - 1) / warps);
         if (grid > needed) grid = std::max(needed, 1);
-        AndJob job{b->and_items.p, b->and_order.p, b->n_and_items, b->and_chunk, b->work_counter.p + 1, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
+        if (RANKED && (b->and_item_scores_k < k || !b->and_item_scores.p)) {      // partial top-k lists: k floats per item
+            CUDA_TRY(b->and_item_scores.alloc(size_t(b->n_and_items) * k));
+            b->and_item_scores_k = k;
+        }
+        AndJob job{b->and_gstart.p, b->and_item_begin.p, b->n_and_items, b->and_chunk, b->work_counter.p + 1, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
         kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, slots);
         b->launches += 1;
     }

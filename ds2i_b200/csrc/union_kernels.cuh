@@ -47,23 +47,6 @@ struct UnionJob {
     float* item_scores;          // nitems * k
 };
 
-// last position p in [0, n) with a[p] <= x (a is non-decreasing, a[0] <= x): 32 probes per step
-__device__ __forceinline__ uint32_t warp_upper_group(const uint32_t* a, uint32_t n, uint32_t x) {
-    const unsigned lane = lane_id();
-    uint32_t lo = 0, hi = n;            // answer in [lo, hi)
-    while (hi - lo > 1) {
-        const uint32_t span = hi - lo;
-        const uint32_t step = (span + 31u) / 32u;
-        const uint32_t p = lo + lane * step;
-        const bool le = p < hi && __ldg(a + p) <= x;
-        const unsigned m = __ballot_sync(FULL, le);          // lane 0 always set
-        const uint32_t f = 31u - __clz(m);
-        lo = lo + f * step;
-        hi = min(hi, lo + step);
-    }
-    return lo;
-}
-
 // top-k with a floor shared across the items of a query
 struct TopKShared {
     TopK t;
