@@ -25,6 +25,7 @@
 #include "query_kernels.cuh"
 #include "and_kernels.cuh"
 #include "union_kernels.cuh"
+#include "decode_kernels.cuh"
 #include "pef_kernels.cuh"
 
 using namespace ds2i_gpu;
@@ -685,82 +686,6 @@ extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int
 // Batched block decode (BASELINE config 2): one warp per 128-posting block, any list, any order.
 constexpr size_t SINGLE_LIST_WARP_BYTES = sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16;
 
-struct DecodeJob {
-    const uint32_t* terms;        // nterms
-    const uint64_t* blk_prefix;   // nterms+1: blocks before list i
-    const uint64_t* out_offsets;  // nterms+1: postings before list i
-    uint32_t* out_docs;
-    uint32_t* out_freqs;
-    uint64_t total_blocks;
-    uint32_t nterms;
-};
-
-template <int CODEC>
-__global__ void __launch_bounds__(256) decode_blocks_kernel(DevIndex idx, DecodeJob job) {
-    s16_table_init(smem_words(0));
-    __syncthreads();
-    typedef BlockEnum<CODEC> E;
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* base = g_smem + S16_TAB_BYTES + warp * SINGLE_LIST_WARP_BYTES;
-    ListState* st = reinterpret_cast<ListState*>(base);
-    uint32_t* stage = reinterpret_cast<uint32_t*>(base + sizeof(ListState));
-    uint32_t* scratch = stage + STAGE_WORDS;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_WORDS);
-    WarpCtx c;
-    ctx_init(c, stage, scratch, bar, idx.codec);
-
-    // a warp takes DECODE_CHUNK consecutive global block ids at a time: one binary search for the
-    // first list of the chunk, then the (list, block) cursor just walks forward
-    constexpr uint64_t DECODE_CHUNK = 32;
-    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
-    const uint64_t nchunks = (job.total_blocks + DECODE_CHUNK - 1) / DECODE_CHUNK;
-    for (uint64_t ch = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp; ch < nchunks; ch += nwarps) {
-        const uint64_t g0 = ch * DECODE_CHUNK, g1 = min(job.total_blocks, g0 + DECODE_CHUNK);
-        uint32_t lo = 0, hi = job.nterms;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (job.blk_prefix[mid] <= g0) lo = mid; else hi = mid;
-        }
-        uint32_t cur_list = 0xffffffffu;
-        uint64_t list_first = 0, list_end = 0, out_base = 0;
-        for (uint64_t g = g0; g < g1; ++g) {
-            while (cur_list == 0xffffffffu || g >= list_end) {
-                if (cur_list != 0xffffffffu) ++lo;
-                cur_list = lo;
-                list_first = job.blk_prefix[lo]; list_end = job.blk_prefix[lo + 1];
-                if (g < list_end) {
-                    ListDir d = idx.dir[job.terms[lo]];
-                    uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-                    __syncwarp();
-                    if (lane == 0) {
-                        st->maxs_off = d.maxs_off;
-                        st->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
-                        st->n = d.n; st->nblocks = nblocks; st->data_bytes = d.data_bytes;
-                    }
-                    __syncwarp();
-                    out_base = job.out_offsets[lo];
-                }
-            }
-            const uint32_t b = uint32_t(g - list_first);
-            // interpolative-coded blocks (list tails; every block of block_interpolative) are bit-serial:
-            // they are decoded one LANE per block by decode_serial_blocks_kernel instead
-            if (idx.codec == CODEC_INTERPOLATIVE || (uint64_t(b) + 1) * BLOCK > st->n) continue;
-            E::decode_docs_block(c, idx, st, b);
-            E::decode_freqs_block(c, idx, st);
-            const uint32_t size = st->cur_size;
-            const uint64_t o = out_base + uint64_t(b) * BLOCK;
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-                uint32_t i = 32 * j + lane;
-                if (i < size) {
-                    job.out_docs[o + i] = st->docs[i];
-                    job.out_freqs[o + i] = st->freqs[i] + 1u;
-                }
-            }
-        }
-    }
-}
-
 // one THREAD per interpolative-coded block, reading the bit stream straight from global memory
 __global__ void __launch_bounds__(128) decode_serial_blocks_kernel(DevIndex idx, DecodeJob job) {
     const uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -821,10 +746,15 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
             pef_decode_launch(*ix->pef, pef_items, pef_nitems, d_terms.p, d_offs.p, d_docs.p, d_freqs.p, ix->sm_count);
         } else {
             DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
-            uint64_t want = (blk[nterms] / 32 + 8) / 8;
+            uint64_t want = (blk[nterms] / 32 + 4) / 4;
             int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
-            if (ix->codec != CODEC_INTERPOLATIVE)
-                decode_blocks_kernel<CODEC_ANY><<<grid, 256, S16_TAB_BYTES + 8 * SINGLE_LIST_WARP_BYTES>>>(ix->dev, job);
+            const size_t dsmem = S16_TAB_BYTES + 4 * DECODE_WARP_BYTES;
+            switch (ix->codec) {
+                case CODEC_OPTPFOR: decode_full_blocks_kernel<CODEC_OPTPFOR><<<grid, 128, dsmem>>>(ix->dev, job); break;
+                case CODEC_VARINT: decode_full_blocks_kernel<CODEC_VARINT><<<grid, 128, dsmem>>>(ix->dev, job); break;
+                case CODEC_QMX: decode_full_blocks_kernel<CODEC_QMX><<<grid, 128, dsmem>>>(ix->dev, job); break;
+                default: break;      // block_interpolative: every block is bit-serial
+            }
             decode_serial_blocks_kernel<<<unsigned((blk[nterms] + 127) / 128), 128>>>(ix->dev, job);
         }
     }

@@ -79,19 +79,26 @@ def pef_bench(args):
                               "postings_per_s": n / (ms * 1e-3), "index_bytes": os.path.getsize(path),
                               "note": "index smaller than the 126 MB L2: this measures L2-resident decode"}), flush=True)
             # next_geq sweeps: lower bounds = docid of every 2^j-th posting + 1
-            offs, docs, _, _ = idx.decode_lists(longest[:256])
+            NL = min(4096, len(longest))
+            offs, docs, _, _ = idx.decode_lists(longest[:NL])
             for j in (0, 3, 6, 9, 12):
-                bounds = []
-                for i in range(256):
+                # every list's bound sequence is cut into runs of CHUNK calls, each run driven through its own
+                # enumerator (opened at the list start): one warp per list alone would leave most of the 148 SMs idle
+                CHUNK = 512
+                bounds, which = [], []
+                for i in range(NL):
                     dd = docs[int(offs[i]):int(offs[i + 1])]
-                    bounds.append(dd[::1 << j].astype(np.uint64) + 1)
+                    bb = dd[::1 << j].astype(np.uint64) + 1
+                    for c0 in range(0, len(bb), CHUNK):
+                        bounds.append(bb[c0:c0 + CHUNK]); which.append(longest[i])
                 calls = sum(len(b) for b in bounds)
+                which = np.asarray(which, dtype=np.uint32)
                 times = []
                 for _ in range(args.warmup + args.steps):
-                    _, _, ms = idx.next_geq_batch(longest[:256], bounds)
+                    _, _, ms = idx.next_geq_batch(which, bounds)
                     times.append(ms)
                 ms = float(np.mean(times[args.warmup:]))
-                print(json.dumps({"bench": "next_geq_sweep", "collection": name, "index_type": t, "skip_postings": 1 << j, "lists": 256, "calls": calls,
+                print(json.dumps({"bench": "next_geq_sweep", "collection": name, "index_type": t, "skip_postings": 1 << j, "lists": NL, "enumerators": len(bounds), "calls": calls,
                                   "kernel_ms": ms, "calls_per_s": calls / (ms * 1e-3), "postings_skipped_per_s": calls * (1 << j) / (ms * 1e-3)}), flush=True)
             idx.close()
 
