@@ -389,8 +389,8 @@ __device__ __noinline__ uint32_t decode_interpolative_prefix(uint32_t win_off, u
 // ---- Binary interpolative block, ONE LANE PER BLOCK --------------------------------------------
 // The code is bit-serial inside a block, but blocks are independent: in the batched decode each lane
 // of a warp takes its own block (list tails in every block index, every block of block_interpolative)
-// straight from global memory.  P (prefix sums) is written to `out` in tree order and converted in
-// place: docids = base + P[i] + i, freqs = P[i] - P[i-1] + 1.  Returns the bytes consumed.
+// straight from global memory.  P (prefix sums) goes to the lane's column of a shared-memory buffer in tree order;
+// the warp then writes every block out together: docids = base + P[i] + i, freqs = P[i] - P[i-1] + 1.
 struct GlobalBitReader {
     const uint32_t* word;   // next aligned word to load
     uint64_t buf;
@@ -413,8 +413,13 @@ struct GlobalBitReader {
     }
 };
 
-__device__ __forceinline__ uint32_t decode_interpolative_lane(const uint8_t* in, uint32_t n, uint32_t sum_of_values, uint32_t* out,
-                                                              bool as_docids, uint32_t docid_base) {
+// P[0..n) of one block -> col[i * SERIAL_STRIDE] (the lane's column of a warp-shared, padded buffer).  The traversal
+// (block_codecs.hpp:101-148 / interpolative_coding.hpp:113-153) is the reference's recursion made iterative; the
+// bounds of a pending range are re-read from the values already decoded (low = P[base-1], high = P[base+cnt]), so
+// the stack holds only (base, cnt) pairs and lives in a 128-bit shift register.  Returns the bytes consumed.
+constexpr uint32_t SERIAL_STRIDE = 33;      // odd stride: the cooperative read-out of one column is conflict-free
+
+__device__ __forceinline__ uint32_t decode_interpolative_lane(const uint8_t* in, uint32_t n, uint32_t sum_of_values, uint32_t* col) {
     const uint8_t* p = in;
     uint32_t sum = sum_of_values;
     if (sum == 0xffffffffu) {                    // TightVariableByte prefix (block_codecs.hpp:131-134)
@@ -425,45 +430,48 @@ __device__ __forceinline__ uint32_t decode_interpolative_lane(const uint8_t* in,
             if (c & 128u) break;
         }
     }
-    out[n - 1] = sum;
+    col[(n - 1) * SERIAL_STRIDE] = sum;
     uint32_t bits = 0;
     if (n > 1) {
         GlobalBitReader br;
         br.init(p);
-        uint32_t stack[32];                      // pending right halves (base, cnt, low, high), depth <= 7
-        int sp = 0;
+        uint64_t stk_lo = 0, stk_hi = 0;         // pending right halves, 16 bits each: base | cnt << 8 (depth <= 7)
+        uint32_t sp = 0;
         uint32_t base = 0, cnt = n - 1, low = 0, high = sum;
         while (true) {
-            uint32_t h = cnt >> 1;
-            uint32_t u = high - low + 1u;
+            const uint32_t h = cnt >> 1;
+            const uint32_t u = high - low + 1u;
             uint32_t val = 0;
             if (u > 1u) {
-                uint32_t nb = 31u - __clz(u);
-                uint32_t m = (nb == 31u) ? (0u - u) : ((2u << nb) - u);
+                const uint32_t nb = 31u - __clz(u);
+                const uint32_t m = (nb == 31u) ? (0u - u) : ((2u << nb) - u);
                 val = br.read(nb);
                 if (val >= m) val = (val << 1) + br.read(1) - m;
             }
             val += low;
-            out[base + h] = val;
-            uint32_t rc = cnt - h - 1u;
+            col[(base + h) * SERIAL_STRIDE] = val;
+            const uint32_t rc = cnt - h - 1u;
             if (h) {
-                if (rc) { stack[4 * sp] = base + h + 1u; stack[4 * sp + 1] = rc; stack[4 * sp + 2] = val; stack[4 * sp + 3] = high; ++sp; }
+                if (rc) {
+                    stk_hi = (stk_hi << 16) | (stk_lo >> 48);
+                    stk_lo = (stk_lo << 16) | uint64_t((base + h + 1u) | (rc << 8));
+                    ++sp;
+                }
                 cnt = h; high = val;
             } else if (rc) {
                 base = base + 1u; cnt = rc; low = val;
             } else {
                 if (!sp) break;
                 --sp;
-                base = stack[4 * sp]; cnt = stack[4 * sp + 1]; low = stack[4 * sp + 2]; high = stack[4 * sp + 3];
+                const uint32_t e = uint32_t(stk_lo) & 0xffffu;
+                stk_lo = (stk_lo >> 16) | (stk_hi << 48);
+                stk_hi >>= 16;
+                base = e & 0xffu; cnt = e >> 8;
+                low = col[(base - 1u) * SERIAL_STRIDE];          // base >= 1: a right half starts behind its parent
+                high = col[(base + cnt) * SERIAL_STRIDE];
             }
         }
         bits = br.consumed_bits;
-    }
-    if (as_docids) {
-        for (uint32_t i = 0; i < n; ++i) out[i] = docid_base + out[i] + i;
-    } else {
-        for (uint32_t i = n - 1; i > 0; --i) out[i] = out[i] - out[i - 1] + 1u;
-        out[0] += 1u;
     }
     return uint32_t(p - in) + ((bits + 7u) >> 3);
 }

@@ -686,30 +686,74 @@ extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int
 // Batched block decode (BASELINE config 2): one warp per 128-posting block, any list, any order.
 constexpr size_t SINGLE_LIST_WARP_BYTES = sizeof(ListState) + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16;
 
-// one THREAD per interpolative-coded block, reading the bit stream straight from global memory
-__global__ void __launch_bounds__(128) decode_serial_blocks_kernel(DevIndex idx, DecodeJob job) {
+// one THREAD per interpolative-coded block, reading the bit stream straight from global memory.  TAILS_ONLY: the job's
+// index codes full blocks with another codec, so only the last, partial block of a list is bit-serial (thread i <-> list i);
+// otherwise (block_interpolative) thread g <-> the g-th block of the job.
+constexpr int SERIAL_WARPS = 2;
+constexpr size_t SERIAL_WARP_BYTES = size_t(BLOCK) * SERIAL_STRIDE * 4;
+
+template <bool TAILS_ONLY>
+__global__ void __launch_bounds__(SERIAL_WARPS * 32) decode_serial_blocks_kernel(DevIndex idx, DecodeJob job) {
+    const unsigned lane = lane_id();
+    uint32_t* buf = reinterpret_cast<uint32_t*>(g_smem) + (threadIdx.x >> 5) * (SERIAL_WARP_BYTES / 4);
+    uint32_t* col = buf + lane;
     const uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= job.total_blocks) return;
-    uint32_t lo = 0, hi = job.nterms;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (job.blk_prefix[mid] <= g) lo = mid; else hi = mid;
+    uint32_t lo = 0, b = 0, size = 0;
+    ListDir d{};
+    bool valid;
+    if (TAILS_ONLY) {
+        valid = g < job.nterms;
+        if (valid) {
+            lo = uint32_t(g);
+            d = idx.dir[job.terms[lo]];
+            valid = d.n % BLOCK != 0;
+            b = (d.n + BLOCK - 1) / BLOCK - 1;
+        }
+    } else {
+        valid = g < job.total_blocks;
+        if (valid) {
+            uint32_t hi = job.nterms;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (job.blk_prefix[mid] <= g) lo = mid; else hi = mid;
+            }
+            b = uint32_t(g - job.blk_prefix[lo]);
+            d = idx.dir[job.terms[lo]];
+        }
     }
-    const uint32_t b = uint32_t(g - job.blk_prefix[lo]);
-    const ListDir d = idx.dir[job.terms[lo]];
-    const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-    const bool partial = (uint64_t(b) + 1) * BLOCK > d.n;
-    if (idx.codec != CODEC_INTERPOLATIVE && !partial) return;
-    const uint32_t size = partial ? d.n % BLOCK : BLOCK;
-    const uint8_t* maxs = idx.lists + d.maxs_off;
-    const uint8_t* ends = maxs + 4ull * nblocks;
-    const uint8_t* data = ends + 4ull * (nblocks - 1);
-    const uint32_t e0 = b ? ldg_u32_unaligned(ends + 4ull * (b - 1)) : 0u;
-    const uint32_t cur_base = (b ? ldg_u32_unaligned(maxs + 4ull * (b - 1)) : 0xffffffffu) + 1u;
-    const uint32_t cur_max = ldg_u32_unaligned(maxs + 4ull * b);
-    const uint64_t o = job.out_offsets[lo] + uint64_t(b) * BLOCK;
-    uint32_t used = decode_interpolative_lane(data + e0, size, cur_max - cur_base - (size - 1u), job.out_docs + o, true, cur_base);
-    decode_interpolative_lane(data + e0 + used, size, 0xffffffffu, job.out_freqs + o, false, 0u);
+    const uint8_t* in = nullptr;
+    uint32_t cur_base = 0;
+    uint64_t o = 0;
+    if (valid) {
+        const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
+        size = ((uint64_t(b) + 1) * BLOCK > d.n) ? d.n % BLOCK : BLOCK;
+        const uint2* bd = idx.bdir + idx.bfirst[job.terms[lo]];
+        const uint2 prev = b ? __ldg(bd + b - 1) : make_uint2(0xffffffffu, 0u);
+        cur_base = prev.x + 1u;
+        const uint32_t cur_max = __ldg(bd + b).x;
+        in = idx.lists + d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1) + prev.y;
+        o = job.out_offsets[lo] + uint64_t(b) * BLOCK;
+        in += decode_interpolative_lane(in, size, cur_max - cur_base - (size - 1u), col);
+    }
+    __syncwarp();
+    // the warp writes the 32 blocks out one after the other: docid_i = base + P[i] + i (block_posting_list.hpp:313-317)
+    for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t n_l = __shfl_sync(FULL, size, l);
+        if (!n_l) continue;
+        const uint32_t base_l = __shfl_sync(FULL, cur_base, l);
+        const uint64_t o_l = (uint64_t(__shfl_sync(FULL, uint32_t(o >> 32), l)) << 32) | __shfl_sync(FULL, uint32_t(o), l);
+        for (uint32_t i = lane; i < n_l; i += 32) job.out_docs[o_l + i] = base_l + buf[i * SERIAL_STRIDE + l] + i;
+    }
+    __syncwarp();
+    if (valid) decode_interpolative_lane(in, size, 0xffffffffu, col);
+    __syncwarp();
+    for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t n_l = __shfl_sync(FULL, size, l);
+        if (!n_l) continue;
+        const uint64_t o_l = (uint64_t(__shfl_sync(FULL, uint32_t(o >> 32), l)) << 32) | __shfl_sync(FULL, uint32_t(o), l);
+        for (uint32_t i = lane; i < n_l; i += 32)
+            job.out_freqs[o_l + i] = buf[i * SERIAL_STRIDE + l] - (i ? buf[(i - 1) * SERIAL_STRIDE + l] : 0u) + 1u;
+    }
 }
 
 extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms,
@@ -755,7 +799,10 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
                 case CODEC_QMX: decode_full_blocks_kernel<CODEC_QMX><<<grid, 128, dsmem>>>(ix->dev, job); break;
                 default: break;      // block_interpolative: every block is bit-serial
             }
-            decode_serial_blocks_kernel<<<unsigned((blk[nterms] + 127) / 128), 128>>>(ix->dev, job);
+            const int st = SERIAL_WARPS * 32;
+            const size_t ssmem = SERIAL_WARPS * SERIAL_WARP_BYTES;
+            if (ix->codec == CODEC_INTERPOLATIVE) decode_serial_blocks_kernel<false><<<unsigned((blk[nterms] + st - 1) / st), st, ssmem>>>(ix->dev, job);
+            else decode_serial_blocks_kernel<true><<<unsigned((nterms + st - 1) / st), st, ssmem>>>(ix->dev, job);
         }
     }
     CUDA_TRY(cudaEventRecord(e1));
