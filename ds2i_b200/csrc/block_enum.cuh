@@ -113,7 +113,15 @@ template <int CODEC>
 __device__ __forceinline__ uint32_t decode_values(WarpCtx& c, uint32_t off, uint32_t size, uint32_t sum_of_values,
                                                   uint32_t* buf, bool& prefix_out) {
     const int codec = (CODEC == CODEC_ANY) ? c.codec : CODEC;
-    if (codec != CODEC_INTERPOLATIVE && size == BLOCK) {
+    if (codec == CODEC_MIXED && size == BLOCK) {
+        // mixed_block::decode (mixed_block.hpp:198-217): block_type byte, then that codec's block
+        const uint32_t type = lds_u8(c.stage, off);
+        prefix_out = type == 2u;
+        if (type == 1u) return 1u + decode_varint128(smem_offset(c.stage), off + 1u, smem_offset(buf));
+        if (type == 0u) return 1u + decode_optpfor128(smem_offset(c.stage), off + 1u, smem_offset(buf), smem_offset(c.scratch));
+        return 1u + decode_interpolative_prefix(smem_offset(c.stage), off + 1u, size, sum_of_values, smem_offset(buf), smem_offset(c.scratch));
+    }
+    if (codec != CODEC_INTERPOLATIVE && codec != CODEC_MIXED && size == BLOCK) {
         prefix_out = false;
         if (codec == CODEC_OPTPFOR) return decode_optpfor128(smem_offset(c.stage), off, smem_offset(buf), smem_offset(c.scratch));
         if (codec == CODEC_VARINT) return decode_varint128(smem_offset(c.stage), off, smem_offset(buf));

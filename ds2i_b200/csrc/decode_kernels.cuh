@@ -84,24 +84,34 @@ __global__ void __launch_bounds__(128, 8) decode_full_blocks_kernel(DevIndex idx
                 const uint32_t prev_max = r ? pm_s : prev.x, e0 = r ? pe_s : prev.y;
                 if (CODEC == CODEC_INTERPOLATIVE || (b + 1u) * BLOCK > d.n) continue;      // bit-serial blocks: the other kernel
                 const uint32_t off = and_stage(idx.lists, data_off + e0, data_off + e1, stage, bar, phase);
-                bool prefix;
-                const uint32_t consumed = and_decode_values<CODEC>(stage_off, off, BLOCK, 0u, docs_off, stack_off, prefix);
-                and_decode_values<CODEC>(stage_off, off + consumed, BLOCK, 0u, freqs_off, stack_off, prefix);
-                {
+                bool dprefix, fprefix;
+                const uint32_t consumed = and_decode_values<CODEC>(stage_off, off, BLOCK, cur_max - prev_max - BLOCK, docs_off, stack_off, dprefix);
+                and_decode_values<CODEC>(stage_off, off + consumed, BLOCK, 0xffffffffu, freqs_off, stack_off, fprefix);
+                uint32_t* od = job.out_docs + out_base + uint64_t(b) * BLOCK + lane;
+                uint32_t* of = job.out_freqs + out_base + uint64_t(b) * BLOCK + lane;
+                if (!dprefix) {
                     uint4 v = reinterpret_cast<uint4*>(docs)[lane];
                     v.y += v.x; v.z += v.y; v.w += v.z;
                     const uint32_t incl = warp_inclusive_scan(v.w);
                     const uint32_t add = prev_max + 1u + (incl - v.w) + 4u * lane;     // docid_i = base + sum_{k<=i} gap_k + i
                     v.x += add; v.y += add + 1u; v.z += add + 2u; v.w += add + 3u;
                     reinterpret_cast<uint4*>(docs)[lane] = v;
-                }
-                __syncwarp();
-                uint32_t* od = job.out_docs + out_base + uint64_t(b) * BLOCK + lane;
-                uint32_t* of = job.out_freqs + out_base + uint64_t(b) * BLOCK + lane;
+                    __syncwarp();
 #pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) {
-                    od[32 * j] = docs[32 * j + lane];
-                    of[32 * j] = freqs[32 * j + lane] + 1u;
+                    for (uint32_t j = 0; j < 4; ++j) od[32 * j] = docs[32 * j + lane];
+                } else {          // interpolative leaves prefix sums (mixed index only)
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) od[32 * j] = prev_max + 1u + docs[32 * j + lane] + 32 * j + lane;
+                }
+                if (!fprefix) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) of[32 * j] = freqs[32 * j + lane] + 1u;
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        const uint32_t i = 32 * j + lane;
+                        of[32 * j] = freqs[i] - (i ? freqs[i - 1] : 0u) + 1u;
+                    }
                 }
                 (void)cur_max;
             }

@@ -150,7 +150,11 @@ static int codec_from_type(const char* t, int* kind) {
     if (s == "block_varint") return CODEC_VARINT;
     if (s == "block_interpolative") return CODEC_INTERPOLATIVE;
     if (s == "block_qmx") return CODEC_QMX;
-    if (s == "opt") { *kind = KIND_PEF; return 0; }
+    if (s == "block_mixed") return CODEC_MIXED;
+    if (s == "opt") { *kind = KIND_PEF; return PEF_VARIANT_OPT; }
+    if (s == "uniform") { *kind = KIND_PEF; return PEF_VARIANT_UNIFORM; }
+    if (s == "single") { *kind = KIND_PEF; return PEF_VARIANT_SINGLE; }
+    if (s == "ef") { *kind = KIND_PEF; return PEF_VARIANT_EF; }
     return -1;
 }
 
@@ -180,7 +184,7 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
         if (kind == KIND_PEF) {
             ix->pef.reset(new PefIndexHost);
             std::string err;
-            int rc = ix->pef->load(p, nbytes, err);
+            int rc = ix->pef->load(p, nbytes, codec, err);
             if (rc != 0) return fail(rc, err);
             ix->size = ix->pef->size; ix->num_docs = ix->pef->num_docs; ix->device_bytes = ix->pef->device_bytes;
             *out = ix.release();
@@ -535,6 +539,7 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
         case CODEC_VARINT: return launch_and_block<CODEC_VARINT, RANKED>(b, db, k);
         case CODEC_INTERPOLATIVE: return launch_and_block<CODEC_INTERPOLATIVE, RANKED>(b, db, k);
         case CODEC_QMX: return launch_and_block<CODEC_QMX, RANKED>(b, db, k);
+        case CODEC_MIXED: return launch_and_block<CODEC_MIXED, RANKED>(b, db, k);
     }
     return fail(DS2I_E_UNSUPPORTED, "unknown codec");
 }
@@ -616,6 +621,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
                 case CODEC_VARINT: rc = launch_union_block<CODEC_VARINT>(b, db, k); break;
                 case CODEC_INTERPOLATIVE: rc = launch_union_block<CODEC_INTERPOLATIVE>(b, db, k); break;
                 case CODEC_QMX: rc = launch_union_block<CODEC_QMX>(b, db, k); break;
+                case CODEC_MIXED: rc = launch_union_block<CODEC_MIXED>(b, db, k); break;
                 default: rc = fail(DS2I_E_UNSUPPORTED, "unknown codec");
             }
         }
@@ -797,6 +803,7 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
                 case CODEC_OPTPFOR: decode_full_blocks_kernel<CODEC_OPTPFOR><<<grid, 128, dsmem>>>(ix->dev, job); break;
                 case CODEC_VARINT: decode_full_blocks_kernel<CODEC_VARINT><<<grid, 128, dsmem>>>(ix->dev, job); break;
                 case CODEC_QMX: decode_full_blocks_kernel<CODEC_QMX><<<grid, 128, dsmem>>>(ix->dev, job); break;
+                case CODEC_MIXED: decode_full_blocks_kernel<CODEC_MIXED><<<grid, 128, dsmem>>>(ix->dev, job); break;
                 default: break;      // block_interpolative: every block is bit-serial
             }
             const int st = SERIAL_WARPS * 32;

@@ -38,6 +38,7 @@ struct PefSeq {             // one bitvector_collection on device
     const PefListDir* lists;
     const PefPart* parts;
     uint32_t log_sampling0, log_sampling1, rb_log_rank1_sampling, rb_log_sampling1;
+    uint32_t raw_ef;        // ef_index: bodies are plain compact_elias_fano / strict_elias_fano (no type bit, zeros sampled)
 };
 
 struct PefIndexDev {
@@ -95,12 +96,17 @@ __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart cons
     b.n = p.size;
     b.universe = p.ub - p.base + 1u;            // last relative value + 1
     b.strict = strict;
-    if (b.universe == b.n) { b.type = PEF_AO; return b; }
-    b.type = uint32_t(__ldg(seq.bits + (p.bit_off >> 6)) >> (p.bit_off & 63)) & 1u;
-    const uint64_t off = p.bit_off + 1;
+    uint64_t off = p.bit_off;
+    if (seq.raw_ef) b.type = PEF_EF;            // compact_elias_fano.hpp:63-136 / strict_elias_fano.hpp:20-36 written directly
+    else {
+        if (b.universe == b.n) { b.type = PEF_AO; return b; }
+        b.type = uint32_t(__ldg(seq.bits + (p.bit_off >> 6)) >> (p.bit_off & 63)) & 1u;
+        off += 1;
+    }
     if (b.type == PEF_EF) {
-        // strict variants never index zeros (strict_sequence.hpp:24-30: ef_log_sampling0 = 63)
-        b.log_s0 = strict ? 63u : seq.log_sampling0;
+        // strict_sequence never indexes zeros (strict_sequence.hpp:24-30: ef_log_sampling0 = 63); strict_elias_fano
+        // used on its own (ef_index) keeps the global sampling
+        b.log_s0 = (strict && !seq.raw_ef) ? 63u : seq.log_sampling0;
         b.log_s1 = seq.log_sampling1;
         uint64_t u = strict ? uint64_t(b.universe) - b.n + 1 : uint64_t(b.universe);
         uint64_t n = b.n;

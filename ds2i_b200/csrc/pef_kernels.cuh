@@ -141,6 +141,12 @@ struct PefEnum {
             PefBody b = pef_open_body(idx.docs, p, false);
             uint32_t from = (part == st->cur_part) ? st->chunk_i0 + st->chunk_size : 0u;
             uint32_t i0 = from;
+            if (i0 >= p.size) {
+                // only single / ef indexes get here (their one "partition" is bounded by the universe, not by its last
+                // value): the cursor's chunk was the last one and the bound lies behind it
+                if (part + 1 < st->d_nparts) { load_chunk(idx, st, part + 1, 0); return st->cur_docid; }
+                return set_end(idx, st);
+            }
             if (p.size - from > 128u) {
                 uint32_t hint = pef_rank_hint(idx.docs, b, lower_bound - p.base);
                 if (hint > i0) i0 = hint;
@@ -150,6 +156,12 @@ struct PefEnum {
                 load_chunk(idx, st, part, i0);
                 if (st->docs[st->chunk_size - 1] >= lower_bound) break;
                 i0 += st->chunk_size;                   // (EF: elements sharing the high part of the bound may span chunks)
+                if (i0 >= p.size) {
+                    // single / ef indexes: the one "partition" is bounded by the universe, not by its last value, so
+                    // the bound may lie behind every element
+                    if (part + 1 < st->d_nparts) { load_chunk(idx, st, part + 1, 0); return st->cur_docid; }
+                    return set_end(idx, st);
+                }
             }
         }
         uint4 v = reinterpret_cast<const uint4*>(st->docs)[lane];
@@ -380,6 +392,57 @@ static inline void pef_parse_sequence(bitvec_view const& bv, uint64_t offset, ui
     }
 }
 
+// uniform_partitioned_sequence header (uniform_partitioned_sequence.hpp:19-103,121-160): as above without the sizes
+// sequence — every partition but the last holds 2^log_partition_size elements
+static inline void pef_parse_uniform_sequence(bitvec_view const& bv, uint64_t offset, uint64_t universe, uint64_t n, global_params const& gp,
+                                              std::vector<PefPart>& out) {
+    bit_cursor it{bv, offset};
+    uint64_t partitions = it.gamma_nonzero();
+    const uint64_t psize = uint64_t(1) << gp.log_partition_size;
+    if (partitions != (n + psize - 1) / psize) throw format_error("bad uniform partition count");
+    if (universe > 0x100000000ull) throw format_error("sequence universe beyond 32 bits");
+    if (partitions == 1) {
+        uint32_t universe_bits = uint32_t(ceil_log2_u64(universe));
+        uint64_t base = it.take(universe_bits);
+        uint64_t ub = 0;
+        if (n > 1) {
+            uint64_t universe_delta = it.delta();
+            ub = universe_delta ? universe_delta : (universe - base - 1);
+        }
+        out.push_back(PefPart{it.pos, 0u, uint32_t(n), uint32_t(base), uint32_t(base + ub)});
+        return;
+    }
+    uint64_t endpoint_bits = it.gamma();
+    uint64_t cur = it.pos;
+    std::vector<uint64_t> ubs = ef_decode_all(bv, cur, universe, partitions + 1, gp);
+    cur += ef_offsets(0, universe, partitions + 1, gp.ef_log_sampling0, gp.ef_log_sampling1).end;
+    uint64_t endpoints_offset = cur;
+    uint64_t sequences_offset = cur + endpoint_bits * (partitions - 1);
+    for (uint64_t p = 0; p < partitions; ++p) {
+        uint64_t endpoint = p ? get_bits(bv, endpoints_offset + (p - 1) * endpoint_bits, uint32_t(endpoint_bits)) : 0;
+        uint64_t begin = p * psize, end = std::min<uint64_t>(n, (p + 1) * psize);
+        uint64_t base = ubs[p] + (p ? 1 : 0), ub = ubs[p + 1];
+        if (ub < base || ub >= universe) throw format_error("partition bounds out of order");
+        out.push_back(PefPart{sequences_offset + endpoint, uint32_t(begin), uint32_t(end - begin), uint32_t(base), uint32_t(ub)});
+    }
+}
+
+// which freq_index instantiation the file holds (index_types.hpp:18-35)
+enum : int { PEF_VARIANT_OPT = 0, PEF_VARIANT_UNIFORM = 1, PEF_VARIANT_SINGLE = 2, PEF_VARIANT_EF = 3 };
+
+static inline void pef_parse_any(int variant, bitvec_view const& bv, uint64_t offset, uint64_t universe, uint64_t n, global_params const& gp,
+                                 std::vector<PefPart>& out) {
+    if (universe > 0x100000000ull) throw format_error("sequence universe beyond 32 bits");
+    switch (variant) {
+        case PEF_VARIANT_OPT: pef_parse_sequence(bv, offset, universe, n, gp, out); break;
+        case PEF_VARIANT_UNIFORM: pef_parse_uniform_sequence(bv, offset, universe, n, gp, out); break;
+        default:
+            // single_index: one indexed_sequence / strict_sequence over the whole list; ef_index: one (strict_)elias_fano.
+            // Both are "one partition with base 0" in the flattened directory.
+            out.push_back(PefPart{offset, 0u, uint32_t(n), 0u, uint32_t(universe - 1)});
+    }
+}
+
 struct PefIndexHost {
     uint64_t size = 0, num_docs = 0, device_bytes = 0;
     struct host_list { uint64_t n; };
@@ -402,7 +465,7 @@ struct PefIndexHost {
     }
 
     // freq_index::map (freq_index.hpp:234-243) + per-list headers (freq_index.hpp:192-214)
-    int load(const uint8_t* p, size_t nbytes, std::string& err) {
+    int load(const uint8_t* p, size_t nbytes, int variant, std::string& err) {
         try {
             byte_reader r(p, nbytes);
             (void)r.get<uint64_t>();
@@ -427,10 +490,10 @@ struct PefIndexHost {
                 if (n == 0 || n > num_docs) throw format_error("bad list length");
                 host_dir[i].n = n;
                 docs.lists[i] = PefListDir{docs.parts.size(), 0u, uint32_t(n)};
-                pef_parse_sequence(dbits, it.pos, num_docs, n, gp, docs.parts);
+                pef_parse_any(variant, dbits, it.pos, num_docs, n, gp, docs.parts);
                 docs.lists[i].nparts = uint32_t(docs.parts.size() - docs.lists[i].first_part);
                 freqs.lists[i] = PefListDir{freqs.parts.size(), 0u, uint32_t(n)};
-                pef_parse_sequence(fbits, fstart[i], occurrences + 1, n, gp, freqs.parts);
+                pef_parse_any(variant, fbits, fstart[i], occurrences + 1, n, gp, freqs.parts);
                 freqs.lists[i].nparts = uint32_t(freqs.parts.size() - freqs.lists[i].first_part);
             }
             int rc = upload(docs, dbits, err);
@@ -442,6 +505,7 @@ struct PefIndexHost {
                 d.bits = s.d_bits; d.lists = s.d_lists; d.parts = s.d_parts;
                 d.log_sampling0 = gp.ef_log_sampling0; d.log_sampling1 = gp.ef_log_sampling1;
                 d.rb_log_rank1_sampling = gp.rb_log_rank1_sampling; d.rb_log_sampling1 = gp.rb_log_sampling1;
+                d.raw_ef = variant == PEF_VARIANT_EF ? 1u : 0u;
                 return d;
             };
             dev.docs = mk(docs); dev.freqs = mk(freqs); dev.num_lists = size; dev.num_docs = uint32_t(num_docs);

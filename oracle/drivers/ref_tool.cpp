@@ -11,6 +11,8 @@
 //   ref_tool bench   <type> <index> <wand> <queries> <op> <threads> [max_queries] [passes]
 //   ref_tool profile <type> <index> <wand> <queries> <op> <out.bin> [max_queries]   (block types only)
 //   ref_tool info    <type> <index>
+//   ref_tool mkmixed block_optpfor <index> <out block_mixed index> [seed]   block types drawn per block; the reference's
+//                    own transformation path (optimal_hybrid_index.cpp:266-292) writes the block_mixed index
 //
 // ops: and, or, ranked_and, wand, maxscore, ranked_or  (queries.hpp:35-591)
 
@@ -319,6 +321,62 @@ int cmd_info(int, char** argv)
     return 0;
 }
 
+// A block_mixed index can only be created by transformation (mixed_block.hpp:32-36).  The reference chooses the block
+// types with its space/time optimiser; for a decode fixture any assignment will do, so the types are drawn per block
+// from a seeded LCG and everything else is the reference's code: get_blocks(), mixed_block::block_transformer,
+// block_posting_list<mixed_block>::write_blocks, block_freq_index::builder.
+static int cmd_mkmixed(int argc, char** argv)
+{
+    block_optpfor_index in;
+    boost::iostreams::mapped_file_source m(argv[3]);
+    succinct::mapper::map(in, m);
+    uint64_t rng = argc > 5 ? std::stoull(argv[5]) : 20261017ull;
+    auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return uint32_t(rng >> 33); };
+    global_parameters params;
+    block_mixed_index::builder builder(in.num_docs(), params);
+    typedef block_optpfor_index::document_enumerator::block_data input_block_type;
+    typedef mixed_block::block_transformer<input_block_type> output_block_type;
+    auto const& possLogs = optpfor_block::codec_type::possLogs;
+    uint64_t counts[3] = {0, 0, 0};
+    std::vector<uint32_t> vals;
+    auto pick = [&](std::vector<uint32_t> const& v, mixed_block::block_type& type, mixed_block::compr_param_type& param) {
+        type = mixed_block::block_type(next() % 3);
+        param = 0;
+        if (type == mixed_block::block_type::pfor) {
+            uint32_t mb = FastPFor::maxbits(v.data(), v.data() + v.size());
+            uint32_t want = mb > next() % 4 ? mb - next() % 4 : 0;             // a few exceptions now and then
+            if (mb > 28 + want) want = mb - 28;                                  // Simple16 codes at most 28 bits
+            uint8_t i = 0;
+            while (i + 1 < possLogs.size() && possLogs[i] < want) ++i;
+            param = i;
+        }
+        counts[size_t(type)] += 1;
+    };
+    for (size_t l = 0; l < in.size(); ++l) {
+        auto e = in[l];
+        auto blocks = e.get_blocks();
+        std::vector<output_block_type> out_blocks;
+        for (auto const& ib : blocks) {
+            mixed_block::block_type dt = mixed_block::block_type::interpolative, ft = dt;
+            mixed_block::compr_param_type dp = 0, fp = 0;
+            if (ib.size == mixed_block::block_size) {
+                ib.decode_doc_gaps(vals); pick(vals, dt, dp);
+                ib.decode_freqs(vals); pick(vals, ft, fp);
+            }
+            out_blocks.emplace_back(ib, dt, ft, dp, fp);
+        }
+        std::vector<uint8_t> buf;
+        block_posting_list<mixed_block>::write_blocks(buf, e.size(), out_blocks);
+        builder.add_posting_list(buf);
+    }
+    block_mixed_index out;
+    builder.build(out);
+    succinct::mapper::freeze(out, argv[4]);
+    printf("{\"lists\": %zu, \"pfor_blocks\": %llu, \"varint_blocks\": %llu, \"interpolative_blocks\": %llu}\n", size_t(in.size()),
+           (unsigned long long)counts[0], (unsigned long long)counts[1], (unsigned long long)counts[2]);
+    return 0;
+}
+
 template <typename Index>
 int dispatch(std::string const& cmd, int argc, char** argv)
 {
@@ -344,6 +402,8 @@ int main(int argc, char** argv)
             std::cerr << "profile: block index types only" << std::endl;
             return 1;
         }
+        if (cmd == "mkmixed") return cmd_mkmixed(argc, argv);
+        if (type == "block_mixed") return dispatch<block_mixed_index>(cmd, argc, argv);
         if (type == "block_optpfor") return dispatch<block_optpfor_index>(cmd, argc, argv);
         if (type == "block_varint") return dispatch<block_varint_index>(cmd, argc, argv);
         if (type == "block_interpolative") return dispatch<block_interpolative_index>(cmd, argc, argv);

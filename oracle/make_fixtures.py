@@ -24,7 +24,7 @@ REF = os.environ.get("DS2I_REFERENCE", "/root/reference")
 BIN = os.path.join(HERE, "_ref")
 DATA = os.path.join(BIN, "data")
 GOLDEN = os.path.join(REPO, "tests", "golden")
-TYPES_FULL = ["block_optpfor", "block_interpolative", "block_varint", "block_qmx", "opt"]
+TYPES_FULL = ["block_optpfor", "block_interpolative", "block_varint", "block_qmx", "opt", "uniform", "single", "ef", "block_mixed"]
 OPS = "and:or:ranked_and:wand:maxscore:ranked_or"
 
 
@@ -67,11 +67,25 @@ def write_collection(prefix, num_docs, docs, freqs, sizes):
 
 def build_all(prefix, out_prefix, types, queries_path):
     for t in types:
-        run(os.path.join(BIN, "create_freq_index"), t, prefix, out_prefix + "." + t + ".idx", "--check")
+        if t == "block_mixed":
+            # only creatable by transformation (mixed_block.hpp:32-36): ref_tool mkmixed re-codes the block_optpfor
+            # index through the reference's own block_transformer / write_blocks with seeded per-block types
+            run(os.path.join(BIN, "ref_tool"), "mkmixed", "block_optpfor", out_prefix + ".block_optpfor.idx", out_prefix + ".block_mixed.idx", "20261017")
+        else:
+            run(os.path.join(BIN, "create_freq_index"), t, prefix, out_prefix + "." + t + ".idx", "--check")
     run(os.path.join(BIN, "create_wand_data"), prefix, out_prefix + ".wand")
     for flavour, tool in (("stock", "ref_tool"), ("strict", "ref_tool_strict")):
         run(os.path.join(BIN, tool), "dump", types[0], out_prefix + "." + types[0] + ".idx", out_prefix + ".wand",
             queries_path, out_prefix + ".expected." + flavour + ".bin", OPS)
+    # every index type holds the same postings, so the reference returns the same bytes for each of them
+    want = open(out_prefix + ".expected.strict.bin", "rb").read()
+    for t in types[1:]:
+        tmp = out_prefix + ".check." + t + ".bin"
+        run(os.path.join(BIN, "ref_tool_strict"), "dump", t, out_prefix + "." + t + ".idx", out_prefix + ".wand", queries_path, tmp, OPS)
+        same = open(tmp, "rb").read() == want
+        os.remove(tmp)
+        if not same:
+            raise RuntimeError("reference results differ between %s and %s" % (types[0], t))
 
 
 def main():
@@ -112,7 +126,7 @@ def main():
     with open(mqp, "w") as g:
         for q in mq:
             g.write("\t".join(str(t) for t in q) + "\n")
-    build_all(tmp, os.path.join(GOLDEN, "mini"), ["block_optpfor", "block_interpolative", "block_varint", "block_qmx", "opt"], mqp)
+    build_all(tmp, os.path.join(GOLDEN, "mini"), TYPES_FULL, mqp)
     np.savez_compressed(os.path.join(GOLDEN, "mini.collection.npz"), num_docs=np.uint64(num_docs),
                         lens=np.array([len(docs[t]) for t in terms], dtype=np.uint64),
                         docs=np.concatenate([docs[t] for t in terms]), freqs=np.concatenate([freqs[t] for t in terms]),
