@@ -369,17 +369,35 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                     }
                     const uint32_t cur_max = s->cur_max;
                     const uint32_t* d = s->docs;
-                    uint32_t hitmask = 0, pos[4];
+                    // the candidates this block answers
+                    uint32_t inb = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        pos[j] = 0;
-                        if ((pending & (1u << j)) && cand[j] <= cur_max) {
-                            pos[j] = lower_bound128(d, cand[j]);
-                            if (d[pos[j]] == cand[j]) hitmask |= 1u << j;
-                            else alive &= ~(1u << j);
-                            pending &= ~(1u << j);
+                    for (int j = 0; j < 4; ++j)
+                        if ((pending & (1u << j)) && cand[j] <= cur_max) inb |= 1u << j;
+                    pending &= ~inb;
+                    const uint32_t nin = __reduce_add_sync(FULL, __popc(inb));
+                    uint32_t hitmask = 0, pos[4] = {0, 0, 0, 0};
+                    if (nin == 1) {
+                        // the usual case when list i is much longer than the driving list: one candidate per block,
+                        // compared with all 128 docids at once instead of a 7-step search on every lane
+                        const uint4 v = reinterpret_cast<const uint4*>(d)[lane];
+                        const uint32_t eq = (v.x == cmin ? 1u : 0u) | (v.y == cmin ? 2u : 0u) | (v.z == cmin ? 4u : 0u) | (v.w == cmin ? 8u : 0u);
+                        const unsigned hb = __ballot_sync(FULL, eq != 0u);
+                        if (hb) {
+                            const uint32_t hl = __ffs(hb) - 1;
+                            const uint32_t p = 4u * hl + __shfl_sync(FULL, uint32_t(__ffs(eq)) - 1u, hl);
+                            hitmask = inb;
+                            pos[0] = pos[1] = pos[2] = pos[3] = p;
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (inb & (1u << j)) {
+                                pos[j] = lower_bound128(d, cand[j]);
+                                if (d[pos[j]] == cand[j]) hitmask |= 1u << j;
+                            }
                     }
+                    alive &= ~(inb & ~hitmask);
                     if (RANKED && __any_sync(FULL, hitmask)) {
                         if (i == 1) {
                             // first term of the sum (queries.hpp:374-379): the driving list's own weight; the

@@ -530,11 +530,6 @@ template <bool RANKED>
 static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     switch (b->index->codec) {
         case CODEC_OPTPFOR:
-            if (const char* ev = getenv("DS2I_GPU_AND_MIN_CTAS")) {      // occupancy experiments
-                if (atoi(ev) == 4) return launch_and_block<CODEC_OPTPFOR, RANKED, 4>(b, db, k);
-                if (atoi(ev) == 5) return launch_and_block<CODEC_OPTPFOR, RANKED, 5>(b, db, k);
-                if (atoi(ev) == 8) return launch_and_block<CODEC_OPTPFOR, RANKED, 8>(b, db, k);
-            }
             return launch_and_block<CODEC_OPTPFOR, RANKED>(b, db, k);
         case CODEC_VARINT: return launch_and_block<CODEC_VARINT, RANKED>(b, db, k);
         case CODEC_INTERPOLATIVE: return launch_and_block<CODEC_INTERPOLATIVE, RANKED>(b, db, k);

@@ -56,9 +56,9 @@ int ds2i_gpu_op_from_name(const char* name);          /* "ranked_and" -> DS2I_OP
 
 /* ---- Index: replaces succinct::mapper::map(index, mapped_file) + the Index concept ------------
  * (queries.cpp:73-77; block_freq_index.hpp:73-134; freq_index.hpp:106-243).
- * index_type is the reference's type name (index_types.hpp:41): block_optpfor, block_varint,
- * block_interpolative, block_qmx, opt.  The compressed bytes are parsed on the host and copied
- * ONCE into HBM of `device`. */
+ * index_type is the reference's type name, every entry of DS2I_INDEX_TYPES (index_types.hpp:41):
+ * ef, single, uniform, opt, block_optpfor, block_varint, block_interpolative, block_mixed, block_qmx.
+ * The compressed bytes are parsed on the host and copied ONCE into HBM of `device`. */
 int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const char* index_type, int device,
                         ds2i_gpu_index** out);
 int ds2i_gpu_index_open_file(const char* path, const char* index_type, int device, ds2i_gpu_index** out);
