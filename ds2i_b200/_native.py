@@ -10,10 +10,10 @@ LIB_PATH = os.path.join(_HERE, "lib", "libds2i_gpu.so")
 SYMBOLS = [
     "ds2i_gpu_last_error", "ds2i_gpu_op_from_name",
     "ds2i_gpu_index_open", "ds2i_gpu_index_open_file", "ds2i_gpu_index_close", "ds2i_gpu_index_size",
-    "ds2i_gpu_index_num_docs", "ds2i_gpu_index_device_bytes", "ds2i_gpu_index_list_sizes",
+    "ds2i_gpu_index_num_docs", "ds2i_gpu_index_device_bytes", "ds2i_gpu_index_set_global_stats", "ds2i_gpu_index_list_sizes",
     "ds2i_gpu_wand_open", "ds2i_gpu_wand_open_file", "ds2i_gpu_wand_close",
-    "ds2i_gpu_query_batch", "ds2i_gpu_batch_prepare", "ds2i_gpu_batch_run", "ds2i_gpu_batch_run_ex", "ds2i_gpu_batch_fetch",
-    "ds2i_gpu_batch_stats", "ds2i_gpu_batch_device_results", "ds2i_gpu_batch_free",
+    "ds2i_gpu_query_batch", "ds2i_gpu_query_batch_docids", "ds2i_gpu_batch_prepare", "ds2i_gpu_batch_run", "ds2i_gpu_batch_run_ex", "ds2i_gpu_batch_fetch", "ds2i_gpu_batch_fetch_docids",
+    "ds2i_gpu_batch_stats", "ds2i_gpu_batch_device_results", "ds2i_gpu_batch_device_docids", "ds2i_gpu_merge_shards", "ds2i_gpu_batch_free",
     "ds2i_gpu_decode_lists", "ds2i_gpu_next_geq_batch",
 ]
 
@@ -43,18 +43,23 @@ def lib():
     for f in (L.ds2i_gpu_index_size, L.ds2i_gpu_index_num_docs, L.ds2i_gpu_index_device_bytes):
         f.argtypes = [vp]
         f.restype = C.c_uint64
+    L.ds2i_gpu_index_set_global_stats.argtypes = [vp, u64p, C.c_size_t, C.c_uint64]
     L.ds2i_gpu_index_list_sizes.argtypes = [vp, u32p, C.c_size_t, u64p]
     L.ds2i_gpu_wand_open.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.ds2i_gpu_wand_open_file.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.ds2i_gpu_wand_close.argtypes = [vp]
     L.ds2i_gpu_wand_close.restype = None
     L.ds2i_gpu_query_batch.argtypes = [vp, vp, C.c_int, C.c_uint32, u32p, u64p, C.c_size_t, u64p, f32p, f32p]
+    L.ds2i_gpu_query_batch_docids.argtypes = [vp, vp, C.c_int, C.c_uint32, u32p, u64p, C.c_size_t, u64p, f32p, u32p, f32p]
     L.ds2i_gpu_batch_prepare.argtypes = [vp, vp, u32p, u64p, C.c_size_t, C.POINTER(vp)]
     L.ds2i_gpu_batch_run.argtypes = [vp, C.c_int, C.c_uint32, f32p]
     L.ds2i_gpu_batch_run_ex.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, f32p]
     L.ds2i_gpu_batch_fetch.argtypes = [vp, u64p, f32p]
+    L.ds2i_gpu_batch_fetch_docids.argtypes = [vp, u32p]
     L.ds2i_gpu_batch_stats.argtypes = [vp, u64p]
     L.ds2i_gpu_batch_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.ds2i_gpu_batch_device_docids.argtypes = [vp, C.POINTER(vp)]
+    L.ds2i_gpu_merge_shards.argtypes = [vp, vp, vp, C.c_uint32, C.c_size_t, C.c_uint32, C.c_int, vp, vp, vp]
     L.ds2i_gpu_batch_free.argtypes = [vp]
     L.ds2i_gpu_batch_free.restype = None
     L.ds2i_gpu_decode_lists.argtypes = [vp, u32p, C.c_size_t, u64p, u32p, u32p, f32p]

@@ -68,6 +68,15 @@ class Index:
     def device_bytes(self):
         return int(_native.lib().ds2i_gpu_index_device_bytes(self._h))
 
+    def set_global_stats(self, df, num_docs_total):
+        """Collection-wide statistics for a document-partitioned shard: df[i] = documents of the WHOLE collection that
+        hold the term of list i (None clears them).  See ds2i_gpu_index_set_global_stats."""
+        if df is None:
+            _native.check(_native.lib().ds2i_gpu_index_set_global_stats(self._h, None, 0, 0))
+            return
+        df = np.ascontiguousarray(df, dtype=np.uint64)
+        _native.check(_native.lib().ds2i_gpu_index_set_global_stats(self._h, _p(df, C.c_uint64), len(df), int(num_docs_total)))
+
     def list_sizes(self, terms):
         terms = np.ascontiguousarray(terms, dtype=np.uint32)
         out = np.zeros(len(terms), dtype=np.uint64)
@@ -168,7 +177,13 @@ class QueryBatch:
         _native.check(_native.lib().ds2i_gpu_batch_fetch(self._h, _p(counts, C.c_uint64), _p(scores, C.c_float)))
         return counts[:self.nq], scores[:self.nq]
 
-    def device_results(self, k=None):
+    def fetch_docids(self):
+        """docids of the scores of the last ranked run (nq x k, 0xffffffff padding) — an extension: the reference keeps scores only."""
+        ids = np.full((max(self.nq, 1), self._k), 0xFFFFFFFF, dtype=np.uint32)
+        _native.check(_native.lib().ds2i_gpu_batch_fetch_docids(self._h, _p(ids, C.c_uint32)))
+        return ids[:self.nq]
+
+    def device_results(self, k=None, with_docids=False):
         """(counts, scores) of the last run as torch CUDA tensors that alias the library's device buffers."""
         import torch
         k = self._k if k is None else k
@@ -182,6 +197,10 @@ class QueryBatch:
         dev = torch.device("cuda", torch.cuda.current_device())
         counts = torch.as_tensor(_Cai(pc.value, (self.nq,), "<i8"), device=dev)
         scores = torch.as_tensor(_Cai(ps.value, (self.nq, k), "<f4"), device=dev)
+        if with_docids:
+            pd = C.c_void_p()
+            _native.check(_native.lib().ds2i_gpu_batch_device_docids(self._h, C.byref(pd)))
+            return counts, scores, torch.as_tensor(_Cai(pd.value, (self.nq, k), "<i4"), device=dev)
         return counts, scores
 
     def stats(self):

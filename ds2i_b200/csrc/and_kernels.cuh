@@ -32,7 +32,7 @@ struct AndJob {
     uint32_t* work_counter;
     uint32_t* item_counts;     // nitems: matches found by the item
     uint32_t* item_sizes;      // nitems: entries in the item's partial top-k
-    float* item_scores;        // nitems * k
+    float* item_scores;        // nitems * 2k: k scores, then the k docids they belong to
 };
 
 // last position p in [0, n) with a[p] <= x (a is non-decreasing, a[0] <= x): 32 probes per step
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                         while (want) {
                             const int src = __ffs(want) - 1;
                             want &= want - 1;
-                            topk.insert(__shfl_sync(FULL, score[j], src));
+                            topk.insert(__shfl_sync(FULL, score[j], src), __shfl_sync(FULL, cand[j], src));
                         }
                     }
                 }
@@ -454,7 +454,10 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         }
 
         if (lane == 0) { job.item_counts[ii] = matches; job.item_sizes[ii] = topk.size; }
-        if (RANKED && lane < k) job.item_scores[size_t(ii) * k + lane] = lane < topk.size ? topk.v : 0.f;
+        if (RANKED && lane < topk.size) {
+            job.item_scores[size_t(ii) * 2 * k + lane] = topk.v;
+            reinterpret_cast<uint32_t*>(job.item_scores)[size_t(ii) * 2 * k + k + lane] = topk.id;
+        }
     }
 
     if (batch.stats && lane == 0) {
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
 // fold the per-item partial results of each query: counts add up, top-k lists merge
 __global__ void __launch_bounds__(128) merge_items_kernel(const uint32_t* item_begin /* nq+1 */, uint32_t nq, const uint32_t* item_counts,
                                                           const uint32_t* item_sizes, const float* item_scores, uint32_t k, bool ranked,
-                                                          uint64_t* out_counts, float* out_scores) {
+                                                          uint64_t* out_counts, float* out_scores, uint32_t* out_docids) {
     const unsigned lane = lane_id();
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -482,16 +485,20 @@ __global__ void __launch_bounds__(128) merge_items_kernel(const uint32_t* item_b
         count += item_counts[it];
         if (ranked) {
             uint32_t n = item_sizes[it];
-            float v = lane < n ? item_scores[size_t(it) * k + lane] : 0.f;
+            float v = lane < n ? item_scores[size_t(it) * 2 * k + lane] : 0.f;
+            uint32_t vid = lane < n ? reinterpret_cast<const uint32_t*>(item_scores)[size_t(it) * 2 * k + k + lane] : 0xffffffffu;
             for (uint32_t j = 0; j < n; ++j) {
                 float sc = __shfl_sync(FULL, v, j);
                 if (!topk.would_enter(sc)) break;       // partial lists are sorted descending
-                topk.insert(sc);
+                topk.insert(sc, __shfl_sync(FULL, vid, j));
             }
         }
     }
     if (lane == 0) out_counts[q] = ranked ? uint64_t(topk.size) : count;
-    if (ranked && lane < k) out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+    if (ranked && lane < k) {
+        out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+        out_docids[size_t(q) * k + lane] = lane < topk.size ? topk.id : 0xffffffffu;
+    }
 }
 
 }  // namespace ds2i_gpu

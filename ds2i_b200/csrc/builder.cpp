@@ -19,6 +19,11 @@
 //   ds2i_build wand  <collection prefix> <out.wand> [threads]
 //   ds2i_build synth <out prefix> <num_docs> <num_terms> <seed> [threads] [nqueries] [types=block_optpfor]
 //        -> <out>.block_optpfor.idx, <out>.wand, <out>.queries without materialising the collection
+//   ds2i_build shard <block_optpfor|block_interpolative> <collection prefix> <out prefix> <G> [threads]
+//        document-partitioned shards: shard g holds the documents [g*N/G, (g+1)*N/G) with local
+//        docids, as an ordinary ds2i index <out>.<g>.idx + wand data <out>.<g>.wand (norm_lens computed with the
+//        collection-wide average length, so BM25 scores equal the unsharded ones) + <out>.<g>.terms (u32 global
+//        term id of every list of the shard: ds2i lists cannot be empty, so absent terms are left out)
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -521,13 +526,19 @@ static inline float doc_term_weight(uint64_t freq, float norm_len) {
 }
 
 // wand_data (wand_data.hpp:16-52): norm_lens then per-list max doc_term_weight
-static void build_wand(list_source const& src, const uint32_t* sizes, std::string const& out_path, unsigned threads) {
-    const uint64_t N = src.num_docs;
+static std::vector<float> compute_norm_lens(const uint32_t* sizes, uint64_t N) {
     std::vector<float> norm_lens(N);
     double lens_sum = 0;
     for (uint64_t i = 0; i < N; ++i) { float len = float(sizes[i]); norm_lens[i] = len; lens_sum += len; }
     float avg_len = float(lens_sum / double(N));
     for (uint64_t i = 0; i < N; ++i) norm_lens[i] /= avg_len;
+    return norm_lens;
+}
+
+static void build_wand(list_source const& src, const uint32_t* sizes, std::string const& out_path, unsigned threads,
+                       const float* given_norm_lens = nullptr) {
+    const uint64_t N = src.num_docs;
+    std::vector<float> norm_lens = given_norm_lens ? std::vector<float>(given_norm_lens, given_norm_lens + N) : compute_norm_lens(sizes, N);
     std::vector<float> max_term_weight(src.num_lists);
     parallel_ranges(src.est_len, threads, [&](size_t, uint64_t lo, uint64_t hi) {
         std::vector<uint32_t> docs, freqs;
@@ -637,7 +648,48 @@ int main(int argc, char** argv) {
             synth_queries(sp, nq, sp.seed + 1, prefix + ".queries");
             return 0;
         }
-        fprintf(stderr, "usage: ds2i_build gen|index|wand|synth ... (see the header of builder.cpp)\n");
+        if (cmd == "shard" && argc >= 6) {
+            std::shared_ptr<mapped> dm, fm;
+            list_source all = collection_source(argv[3], dm, fm);
+            mapped sm(std::string(argv[3]) + ".sizes");
+            if (sm.words() < 1 + all.num_docs) throw std::runtime_error("bad .sizes");
+            const uint64_t G = strtoull(argv[5], nullptr, 10);
+            if (G < 1 || G > all.num_docs) throw std::invalid_argument("bad shard count");
+            unsigned threads = argc > 6 ? unsigned(atoi(argv[6])) : hw;
+            const std::vector<float> norm_lens = compute_norm_lens(sm.u32() + 1, all.num_docs);     // collection-wide average
+            std::string out = argv[4];
+            for (uint64_t g = 0; g < G; ++g) {
+                const uint32_t lo = uint32_t(all.num_docs * g / G), hi = uint32_t(all.num_docs * (g + 1) / G);
+                // the terms that occur in the shard, and how often
+                std::vector<uint32_t> terms;
+                list_source sh;
+                std::vector<uint32_t> d, f;
+                for (uint64_t t = 0; t < all.num_lists; ++t) {
+                    all.get(t, d, f);
+                    size_t a = std::lower_bound(d.begin(), d.end(), lo) - d.begin(), b = std::lower_bound(d.begin(), d.end(), hi) - d.begin();
+                    if (b > a) { terms.push_back(uint32_t(t)); sh.est_len.push_back(b - a); }
+                }
+                if (terms.empty()) throw std::runtime_error("shard without postings");
+                sh.num_docs = hi - lo; sh.num_lists = terms.size();
+                auto tp = std::make_shared<std::vector<uint32_t>>(terms);
+                sh.get = [all, tp, lo, hi](uint64_t i, std::vector<uint32_t>& docs, std::vector<uint32_t>& freqs) {
+                    std::vector<uint32_t> d2, f2;
+                    all.get((*tp)[i], d2, f2);
+                    size_t a = std::lower_bound(d2.begin(), d2.end(), lo) - d2.begin(), b = std::lower_bound(d2.begin(), d2.end(), hi) - d2.begin();
+                    docs.resize(b - a); freqs.assign(f2.begin() + a, f2.begin() + b);
+                    for (size_t k = a; k < b; ++k) docs[k - a] = d2[k] - lo;
+                };
+                std::string base = out + "." + std::to_string(g);
+                build_block_index(sh, parse_codec(argv[2]), base + ".idx", threads, nullptr);
+                build_wand(sh, nullptr, base + ".wand", threads, norm_lens.data() + lo);
+                FILE* ft = fopen((base + ".terms").c_str(), "wb");
+                if (!ft) throw std::runtime_error("cannot write " + base + ".terms");
+                fwrite(terms.data(), 4, terms.size(), ft);
+                fclose(ft);
+            }
+            return 0;
+        }
+        fprintf(stderr, "usage: ds2i_build gen|index|wand|synth|shard ... (see the header of builder.cpp)\n");
         return 1;
     } catch (std::exception const& e) {
         fprintf(stderr, "ds2i_build: %s\n", e.what());

@@ -95,6 +95,9 @@ struct ds2i_gpu_index {
     int codec = CODEC_OPTPFOR;
     uint64_t size = 0, num_docs = 0;
     uint64_t device_bytes = 0;
+    // collection-wide statistics of a document-partitioned shard (empty / 0: the index is the whole collection)
+    std::vector<uint64_t> g_df;
+    uint64_t g_num_docs = 0;
     // block indexes
     std::vector<ListDir> host_dir;
     dev_buf<uint8_t> d_lists;
@@ -126,6 +129,7 @@ struct ds2i_gpu_batch {
     dev_buf<float> q_weight, max_weight, out_scores;
     dev_buf<uint8_t> ord_size, ord_maxw;
     dev_buf<uint64_t> out_counts;
+    dev_buf<uint32_t> out_docids;
     dev_buf<unsigned long long> stats;
     // block-at-a-time conjunctive path: work items = (query, chunk of blocks of its shortest list)
     dev_buf<uint32_t> and_gstart, and_item_begin, and_item_counts, and_item_sizes;
@@ -254,6 +258,18 @@ static inline uint64_t list_size_of(const ds2i_gpu_index* ix, uint32_t term) {
     return ix->kind == KIND_PEF ? ix->pef->host_dir[term].n : ix->host_dir[term].n;
 }
 
+extern "C" int ds2i_gpu_index_set_global_stats(ds2i_gpu_index* ix, const uint64_t* df, size_t nterms, uint64_t num_docs_total) {
+    if (!ix) return fail(DS2I_E_ARG, "null index");
+    if (!df) { ix->g_df.clear(); ix->g_num_docs = 0; return DS2I_OK; }          // back to the index's own statistics
+    if (nterms != ix->size) return fail(DS2I_E_ARG, "one document frequency per list of the index expected");
+    if (num_docs_total < ix->num_docs) return fail(DS2I_E_ARG, "the collection cannot be smaller than its shard");
+    for (size_t i = 0; i < nterms; ++i)
+        if (df[i] < list_size_of(ix, uint32_t(i)) || df[i] > num_docs_total) return fail(DS2I_E_ARG, "document frequency out of range for list " + std::to_string(i));
+    ix->g_df.assign(df, df + nterms);
+    ix->g_num_docs = num_docs_total;
+    return DS2I_OK;
+}
+
 extern "C" int ds2i_gpu_index_list_sizes(const ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms, uint64_t* out_sizes) {
     if (!ix || (!terms && nterms) || (!out_sizes && nterms)) return fail(DS2I_E_ARG, "null argument");
     for (size_t i = 0; i < nterms; ++i) {
@@ -315,7 +331,11 @@ static int cached_blocks_per_sm(const void* kern, int threads, size_t smem, int*
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     for (auto const& c : cache) if (c.k == kern && c.s == smem) { *out = c.v; return DS2I_OK; }
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // the opt-in limit is per-function state and the last call wins: only ever raise it, or a batch with few terms
+    // would lower it under a later batch that needs the larger window again
+    size_t raised = 0;
+    for (auto const& c : cache) if (c.k == kern) raised = std::max(raised, c.s);
+    if (smem > raised) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     cache.push_back(key{kern, smem, per_sm});
@@ -346,7 +366,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     std::vector<float> q_weight, max_weight;
     std::vector<uint8_t> ord_size, ord_maxw;
     std::vector<uint64_t> cost(nq, 0), shortest(nq, 0);
-    struct ent { uint64_t n; float mw; uint8_t pos; };
+    struct ent { uint64_t n; float mw; uint8_t pos; uint64_t local_n; };   // n: the list size the reference would see (collection-wide df for a shard)
     std::vector<uint32_t> tmp;
     std::vector<ent> ents;
     int max_terms = 1;
@@ -361,14 +381,16 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
             uint32_t t = tmp[i];
             if (t >= ix->size) return fail(DS2I_E_ARG, "term id out of range in query " + std::to_string(q));
             if (wand && t >= wand->num_terms) return fail(DS2I_E_ARG, "term id beyond wand data");
-            uint64_t n = list_size_of(ix, t);
-            float qw = query_term_weight(j - i, n, ix->num_docs);
+            const uint64_t local_n = list_size_of(ix, t);
+            // a document-partitioned shard scores with the statistics of the whole collection (ds2i_gpu_index_set_global_stats)
+            const uint64_t n = ix->g_df.empty() ? local_n : ix->g_df[t];
+            float qw = query_term_weight(j - i, n, ix->g_num_docs ? ix->g_num_docs : ix->num_docs);
             float mw = wand ? qw * wand->h_max_term_weight[t] : 0.f;
             if (ents.size() >= size_t(MAX_TERMS))
                 return fail(DS2I_E_LIMIT, "query " + std::to_string(q) + " has more than " + std::to_string(MAX_TERMS) + " distinct terms");
-            ents.push_back(ent{n, mw, uint8_t(ents.size())});
+            ents.push_back(ent{n, mw, uint8_t(ents.size()), local_n});
             term.push_back(t); q_weight.push_back(qw); max_weight.push_back(mw);
-            cost[q] += n;
+            cost[q] += local_n;
             i = j;
         }
         max_terms = std::max<int>(max_terms, int(ents.size()));
@@ -379,7 +401,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         std::sort(by_mw.begin(), by_mw.end(), [](ent const& l, ent const& r) { return l.mw < r.mw; });
         for (auto const& e : by_size) ord_size.push_back(e.pos);
         for (auto const& e : by_mw) ord_maxw.push_back(e.pos);
-        shortest[q] = ents.empty() ? 0 : by_size[0].n;
+        shortest[q] = ents.empty() ? 0 : by_size[0].local_n;
     }
     std::iota(sched.begin(), sched.end(), 0u);
     std::stable_sort(sched.begin(), sched.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
@@ -464,7 +486,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     CUDA_TRY(b->q_weight.upload(q_weight)); CUDA_TRY(b->max_weight.upload(max_weight));
     CUDA_TRY(b->ord_size.upload(ord_size)); CUDA_TRY(b->ord_maxw.upload(ord_maxw));
     CUDA_TRY(b->work_counter.alloc(4));
-    CUDA_TRY(b->out_counts.alloc(nq)); CUDA_TRY(b->out_scores.alloc(nq * MAX_K));
+    CUDA_TRY(b->out_counts.alloc(nq)); CUDA_TRY(b->out_scores.alloc(nq * MAX_K)); CUDA_TRY(b->out_docids.alloc(nq * MAX_K));
     CUDA_TRY(b->stats.alloc(8));
     CUDA_TRY(cudaMemset(b->stats.p, 0, 8 * sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreate(&b->ev0)); CUDA_TRY(cudaEventCreate(&b->ev1));
@@ -512,7 +534,7 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
         int needed = int((b->n_and_items + warps - 1) / warps);
         if (grid > needed) grid = std::max(needed, 1);
         if (RANKED && (b->and_item_scores_k < k || !b->and_item_scores.p)) {      // partial top-k lists: k floats per item
-            CUDA_TRY(b->and_item_scores.alloc(size_t(b->n_and_items) * k));
+            CUDA_TRY(b->and_item_scores.alloc(size_t(b->n_and_items) * 2 * k));
             b->and_item_scores_k = k;
         }
         AndJob job{b->and_gstart.p, b->and_item_begin.p, b->n_and_items, b->and_chunk, b->work_counter.p + 1, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
@@ -520,7 +542,7 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
         b->launches += 1;
     }
     merge_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->and_item_begin.p, b->nq, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p,
-                                                 k, RANKED, b->out_counts.p, b->out_scores.p);
+                                                 k, RANKED, b->out_counts.p, b->out_scores.p, b->out_docids.p);
     return DS2I_OK;   // the caller counts the merge launch
 }
 
@@ -558,13 +580,13 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
     int needed = int((b->n_un_items + warps - 1) / warps);
     if (grid > needed) grid = std::max(needed, 1);
     if (b->un_item_scores_k < k || !b->un_item_scores.p) {      // partial top-k lists: k floats per item
-        CUDA_TRY(b->un_item_scores.alloc(size_t(b->n_un_items) * k));
+        CUDA_TRY(b->un_item_scores.alloc(size_t(b->n_un_items) * 2 * k));
         b->un_item_scores_k = k;
     }
     CUDA_TRY(cudaMemsetAsync(b->un_threshold.p, 0, std::max<size_t>(b->nq, 1) * sizeof(uint32_t)));
     UnionJob job{b->un_gstart.p, b->un_gterm.p, b->un_gquery.p, b->un_gbase.p, b->un_ub.p, b->n_un_groups, b->n_un_items, b->un_item_blocks, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
     if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, b->wand->dev, db, job, k, b->max_terms); b->launches += 1; }
-    merge_union_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_scores.p, k, b->out_counts.p, b->out_scores.p);
+    merge_union_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_scores.p, k, b->out_counts.p, b->out_scores.p, b->out_docids.p);
     return DS2I_OK;
 }
 
@@ -599,7 +621,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     db.nq = b->nq; db.q_begin = b->q_begin.p; db.term = b->term.p; db.q_weight = b->q_weight.p;
     db.max_weight = b->max_weight.p; db.ord_size = b->ord_size.p; db.ord_maxw = b->ord_maxw.p;
     db.sched = b->sched.p; db.work_counter = b->work_counter.p; db.out_counts = b->out_counts.p;
-    db.out_scores = b->out_scores.p; db.stats = b->stats.p;
+    db.out_scores = b->out_scores.p; db.out_docids = b->out_docids.p; db.stats = b->stats.p;
     CUDA_TRY(cudaMemsetAsync(b->stats.p, 0, 8 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, 4 * sizeof(uint32_t)));
     CUDA_TRY(cudaEventRecord(b->ev0));
@@ -643,6 +665,14 @@ extern "C" int ds2i_gpu_batch_fetch(ds2i_gpu_batch* b, uint64_t* out_counts, flo
     return DS2I_OK;
 }
 
+extern "C" int ds2i_gpu_batch_fetch_docids(ds2i_gpu_batch* b, uint32_t* out_docids) {
+    if (!b || !out_docids) return fail(DS2I_E_ARG, "null argument");
+    if (!b->last_ranked) return fail(DS2I_E_ARG, "the last operator run on this batch was not a ranked one");
+    CUDA_TRY(cudaSetDevice(b->index->device));
+    if (b->nq) CUDA_TRY(cudaMemcpy(out_docids, b->out_docids.p, size_t(b->nq) * b->last_k * 4, cudaMemcpyDeviceToHost));
+    return DS2I_OK;
+}
+
 extern "C" int ds2i_gpu_batch_stats(ds2i_gpu_batch* b, uint64_t out_stats[8]) {
     if (!b || !out_stats) return fail(DS2I_E_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(b->index->device));
@@ -660,11 +690,69 @@ extern "C" int ds2i_gpu_batch_device_results(ds2i_gpu_batch* b, void** d_counts,
     return DS2I_OK;
 }
 
+extern "C" int ds2i_gpu_batch_device_docids(ds2i_gpu_batch* b, void** d_docids) {
+    if (!b || !d_docids) return fail(DS2I_E_ARG, "null argument");
+    *d_docids = b->out_docids.p;
+    return DS2I_OK;
+}
+
 extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { delete b; }
+
+// ------------------------------------------------------------------------------------------------
+// Document-partitioned shards: fold the per-shard results of one query batch.  Shards hold disjoint
+// documents, so match counts add up and the global top-k is the top-k of the shards' top-k lists.
+__global__ void __launch_bounds__(128) merge_shards_kernel(const uint64_t* counts, const float* scores, const uint32_t* docids, uint32_t nshards,
+                                                           uint32_t nq, uint32_t k, bool ranked, uint64_t* out_counts, float* out_scores,
+                                                           uint32_t* out_docids) {
+    const unsigned lane = lane_id();
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    uint64_t total = 0;
+    TopK topk;
+    topk.init(ranked ? k : 1u);
+    for (uint32_t s = 0; s < nshards; ++s) {
+        const size_t row = size_t(s) * nq + q;
+        const uint64_t c = counts[row];
+        total += c;
+        if (!ranked) continue;
+        const uint32_t n = uint32_t(c < k ? c : k);
+        const float v = lane < n ? scores[row * k + lane] : 0.f;
+        const uint32_t id = lane < n ? docids[row * k + lane] : 0xffffffffu;
+        for (uint32_t j = 0; j < n; ++j) {
+            const float sc = __shfl_sync(FULL, v, j);
+            if (!topk.would_enter(sc)) break;          // per-shard lists are sorted descending
+            topk.insert(sc, __shfl_sync(FULL, id, j));
+        }
+    }
+    if (lane == 0) out_counts[q] = ranked ? uint64_t(topk.size) : total;
+    if (ranked && lane < k) {
+        out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+        out_docids[size_t(q) * k + lane] = lane < topk.size ? topk.id : 0xffffffffu;
+    }
+}
+
+extern "C" int ds2i_gpu_merge_shards(const uint64_t* d_counts, const float* d_scores, const uint32_t* d_docids, uint32_t nshards, size_t nq,
+                                     uint32_t k, int ranked, uint64_t* d_out_counts, float* d_out_scores, uint32_t* d_out_docids) {
+    if (!d_counts || !d_out_counts || (ranked && (!d_scores || !d_docids || !d_out_scores || !d_out_docids))) return fail(DS2I_E_ARG, "null argument");
+    if (ranked && (k < 1 || k > MAX_K)) return fail(DS2I_E_LIMIT, "k must be in 1.." + std::to_string(MAX_K));
+    if (nq > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many queries in one batch");
+    if (nq && nshards)
+        merge_shards_kernel<<<unsigned((nq + 3) / 4), 128>>>(d_counts, d_scores, d_docids, nshards, uint32_t(nq), k, ranked != 0, d_out_counts,
+                                                             d_out_scores, d_out_docids);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return DS2I_OK;
+}
 
 extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int op, uint32_t k,
                                     const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
                                     uint64_t* out_counts, float* out_scores, float* out_elapsed_ms) {
+    return ds2i_gpu_query_batch_docids(ix, wand, op, k, terms, query_offsets, nq, out_counts, out_scores, nullptr, out_elapsed_ms);
+}
+
+extern "C" int ds2i_gpu_query_batch_docids(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int op, uint32_t k,
+                                           const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
+                                           uint64_t* out_counts, float* out_scores, uint32_t* out_docids, float* out_elapsed_ms) {
     const bool trace = trace_on();
     double t0 = now_ms();
     ds2i_gpu_batch* b = nullptr;
@@ -677,6 +765,7 @@ extern "C" int ds2i_gpu_query_batch(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, int
     if (rc != DS2I_OK) return rc;
     double t2 = now_ms();
     rc = ds2i_gpu_batch_fetch(b, out_counts, out_scores);
+    if (rc == DS2I_OK && out_docids && b->last_ranked) rc = ds2i_gpu_batch_fetch_docids(b, out_docids);
     double t3 = now_ms();
     guard.reset();
     if (trace) fprintf(stderr, "[ds2i_gpu] query_batch nq=%zu prepare %.2f ms, run %.2f ms, fetch %.2f ms, free %.2f ms\n", nq, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);

@@ -30,6 +30,7 @@ struct DevBatch {
     uint32_t* work_counter;
     uint64_t* out_counts;        // nq
     float* out_scores;           // nq * k
+    uint32_t* out_docids;        // nq * k: docid of every score
     unsigned long long* stats;   // 8 counters or nullptr
 };
 
@@ -39,22 +40,26 @@ __device__ __forceinline__ float doc_term_weight(uint32_t freq, float norm_len) 
     return f / (f + 1.2f * (0.5f + 0.5f * norm_len));
 }
 
-// topk_queue (queries.hpp:152-197): the k largest scores, kept sorted descending across lanes
+// topk_queue (queries.hpp:152-197): the k largest scores, kept sorted descending across lanes.  The reference keeps
+// scores only; here every entry also carries its docid (what a caller needs to fetch the documents, and what a
+// doc-partitioned deployment merges on) — it rides along and never influences which scores are kept.
 struct TopK {
     float v;          // lane i holds the i-th largest score
+    uint32_t id;      // ... and the docid it belongs to
     uint32_t size, k;
     float thr;        // k-th largest, valid when size == k
-    __device__ __forceinline__ void init(uint32_t k_) { v = 0.f; size = 0; k = k_; thr = 0.f; }
+    __device__ __forceinline__ void init(uint32_t k_) { v = 0.f; id = 0xffffffffu; size = 0; k = k_; thr = 0.f; }
     __device__ __forceinline__ bool would_enter(float s) const { return size < k || s > thr; }
-    __device__ __forceinline__ bool insert(float s) {
+    __device__ __forceinline__ bool insert(float s, uint32_t docid) {
         if (!would_enter(s)) return false;
         const unsigned lane = lane_id();
         unsigned ge = __ballot_sync(FULL, lane < size && v >= s);
         uint32_t pos = __popc(ge);
         float up = __shfl_up_sync(FULL, v, 1);
+        uint32_t upid = __shfl_up_sync(FULL, id, 1);
         uint32_t nsize = size < k ? size + 1 : k;
-        if (lane > pos && lane < nsize) v = up;
-        if (lane == pos) v = s;
+        if (lane > pos && lane < nsize) { v = up; id = upid; }
+        if (lane == pos) { v = s; id = docid; }
         size = nsize;
         thr = __shfl_sync(FULL, v, k - 1);
         return true;
@@ -153,7 +158,7 @@ __device__ __forceinline__ void run_queries(typename E::Index const& idx, DevWan
                             float norm_len = wand.norm_lens[candidate];
                             float score = 0.f;
                             for (i = 0; i < nt; ++i) score += ws->qw[i] * doc_term_weight(E::freq(c, idx, &st[i]), norm_len);
-                            topk.insert(score);
+                            topk.insert(score, candidate);
                             c.c_scored += 1;
                         }
                         candidate = E::next(c, idx, &st[0]);
@@ -178,7 +183,7 @@ __device__ __forceinline__ void run_queries(typename E::Index const& idx, DevWan
                         }
                         next_doc = min(next_doc, d);
                     }
-                    if (OP == OP_RANKED_OR) topk.insert(score);
+                    if (OP == OP_RANKED_OR) topk.insert(score, cur_doc);
                     cur_doc = next_doc;
                 }
             } else if (OP == OP_WAND) {
@@ -215,7 +220,7 @@ __device__ __forceinline__ void run_queries(typename E::Index const& idx, DevWan
                             score += ws->qw[s] * doc_term_weight(E::freq(c, idx, &st[s]), norm_len);
                             E::next(c, idx, &st[s]);
                         }
-                        topk.insert(score);
+                        topk.insert(score, pivot_id);
                         c.c_scored += 1;
                         sort_enums();
                     } else {
@@ -258,7 +263,7 @@ __device__ __forceinline__ void run_queries(typename E::Index const& idx, DevWan
                         if (d == cur_doc) score += ws->qw[i] * doc_term_weight(E::freq(c, idx, &st[i]), norm_len);
                     }
                     c.c_scored += 1;
-                    if (topk.insert(score)) {
+                    if (topk.insert(score, cur_doc)) {
                         while (non_essential < nt && !topk.would_enter(ws->ub[non_essential])) non_essential += 1;
                     }
                     cur_doc = next_doc;
@@ -267,7 +272,10 @@ __device__ __forceinline__ void run_queries(typename E::Index const& idx, DevWan
         }
 
         if (lane == 0) batch.out_counts[q] = RANKED ? uint64_t(topk.size) : results;
-        if (RANKED && lane < k) batch.out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+        if (RANKED && lane < k) {
+            batch.out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+            batch.out_docids[size_t(q) * k + lane] = lane < topk.size ? topk.id : 0xffffffffu;
+        }
     }
 
     if (batch.stats && lane == 0) {

@@ -44,7 +44,7 @@ struct UnionJob {
     uint32_t* work_counter;
     uint32_t* query_threshold;   // nq: float bits of the best published k-th score of the query
     uint32_t* item_sizes;
-    float* item_scores;          // nitems * k
+    float* item_scores;          // nitems * 2k: k scores, then the k docids they belong to
 };
 
 // top-k with a floor shared across the items of a query
@@ -54,7 +54,7 @@ struct TopKShared {
     __device__ __forceinline__ void init(uint32_t k) { t.init(k); floor_ = 0.f; }
     __device__ __forceinline__ float bar() const { return t.size < t.k ? floor_ : fmaxf(t.thr, floor_); }
     __device__ __forceinline__ bool would_enter(float s) const { return s > bar(); }
-    __device__ __forceinline__ void insert(float s) { if (would_enter(s)) t.insert(s); }
+    __device__ __forceinline__ void insert(float s, uint32_t docid) { if (would_enter(s)) t.insert(s, docid); }
 };
 
 struct UnionWarp {
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                     while (want) {
                         const int src = __ffs(want) - 1;
                         want &= want - 1;
-                        topk.insert(__shfl_sync(FULL, score[j], src));
+                        topk.insert(__shfl_sync(FULL, score[j], src), __shfl_sync(FULL, cand[j], src));
                     }
                 }
                 if (topk.t.size == topk.t.k && topk.t.thr > published) {
@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
         }
 
         if (lane == 0) job.item_sizes[rslot] = topk.t.size;
-        if (lane < topk.t.size) job.item_scores[size_t(rslot) * k + lane] = topk.t.v;
+        if (lane < topk.t.size) {
+            job.item_scores[size_t(rslot) * 2 * k + lane] = topk.t.v;
+            reinterpret_cast<uint32_t*>(job.item_scores)[size_t(rslot) * 2 * k + k + lane] = topk.t.id;
+        }
     }
 
     if (batch.stats && lane == 0) {
@@ -304,7 +307,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
 
 // fold the per-item partial top-k lists of each query (most items of a pruned list are empty: 32 sizes per load)
 __global__ void __launch_bounds__(128) merge_union_items_kernel(const uint32_t* item_begin /* nq+1 */, uint32_t nq, const uint32_t* item_sizes,
-                                                                const float* item_scores, uint32_t k, uint64_t* out_counts, float* out_scores) {
+                                                                const float* item_scores, uint32_t k, uint64_t* out_counts, float* out_scores,
+                                                                uint32_t* out_docids) {
     const unsigned lane = lane_id();
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -320,16 +324,20 @@ __global__ void __launch_bounds__(128) merge_union_items_kernel(const uint32_t* 
             nz &= nz - 1;
             const uint32_t n = __shfl_sync(FULL, n_l, src);
             const uint32_t it = base + src;
-            const float v = lane < n ? item_scores[size_t(it) * k + lane] : 0.f;
+            const float v = lane < n ? item_scores[size_t(it) * 2 * k + lane] : 0.f;
+            const uint32_t vid = lane < n ? reinterpret_cast<const uint32_t*>(item_scores)[size_t(it) * 2 * k + k + lane] : 0xffffffffu;
             for (uint32_t j = 0; j < n; ++j) {
                 const float sc = __shfl_sync(FULL, v, j);
                 if (!topk.would_enter(sc)) break;       // partial lists are sorted descending
-                topk.insert(sc);
+                topk.insert(sc, __shfl_sync(FULL, vid, j));
             }
         }
     }
     if (lane == 0) out_counts[q] = uint64_t(topk.size);
-    if (lane < k) out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+    if (lane < k) {
+        out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
+        out_docids[size_t(q) * k + lane] = lane < topk.size ? topk.id : 0xffffffffu;
+    }
 }
 
 }  // namespace ds2i_gpu

@@ -67,6 +67,12 @@ uint64_t ds2i_gpu_index_size(const ds2i_gpu_index*);       /* Index::size()     
 uint64_t ds2i_gpu_index_num_docs(const ds2i_gpu_index*);   /* Index::num_docs()                          */
 uint64_t ds2i_gpu_index_device_bytes(const ds2i_gpu_index*);
 /* document_enumerator::size() of index[term] for each term (block_posting_list.hpp:178-181). */
+/* Document-partitioned deployment: the index holds the documents of ONE shard.  BM25 needs the
+ * statistics of the whole collection — bm25::query_term_weight(qtf, df, num_docs) (bm25.hpp:17-24) and the order in
+ * which ranked_and_query sums its terms (lists by increasing size, queries.hpp:357-360) — so the caller supplies, for
+ * every list of this index, the document frequency over all shards, and the total number of documents.  With them
+ * every score equals the one the reference computes on the unsharded collection.  df == NULL clears them. */
+int ds2i_gpu_index_set_global_stats(ds2i_gpu_index*, const uint64_t* df, size_t nterms, uint64_t num_docs_total);
 int ds2i_gpu_index_list_sizes(const ds2i_gpu_index*, const uint32_t* terms, size_t nterms, uint64_t* out_sizes);
 
 /* ---- wand_data: replaces succinct::mapper::map(wdata, md) (queries.cpp:90-95; wand_data.hpp:55-78). */
@@ -84,6 +90,10 @@ void ds2i_gpu_wand_close(ds2i_gpu_wand*);
 int ds2i_gpu_query_batch(ds2i_gpu_index*, ds2i_gpu_wand*, int op, uint32_t k,
                          const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
                          uint64_t* out_counts, float* out_scores, float* out_elapsed_ms);
+/* the same with the docid of every score (nq * k, 0xffffffff padding; out_docids may be NULL) */
+int ds2i_gpu_query_batch_docids(ds2i_gpu_index*, ds2i_gpu_wand*, int op, uint32_t k,
+                                const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
+                                uint64_t* out_counts, float* out_scores, uint32_t* out_docids, float* out_elapsed_ms);
 
 /* The same in three steps, for callers that keep a batch resident in HBM and run several
  * operators over it (what op_perftest does with its `queries` vector, queries.cpp:97-121). */
@@ -99,6 +109,10 @@ int ds2i_gpu_batch_run(ds2i_gpu_batch*, int op, uint32_t k, float* out_elapsed_m
 #define DS2I_RUN_FAITHFUL 1u
 int ds2i_gpu_batch_run_ex(ds2i_gpu_batch*, int op, uint32_t k, uint32_t flags, float* out_elapsed_ms);
 int ds2i_gpu_batch_fetch(ds2i_gpu_batch*, uint64_t* out_counts, float* out_scores);   /* D2H of the last run */
+/* docids of the scores of the last (ranked) run, nq * k, same layout as out_scores, 0xffffffff where a query has
+ * fewer than k results.  The reference's topk_queue keeps scores only (queries.hpp:157-172); a caller that has to
+ * fetch the documents — or merge the results of document-partitioned shards — needs the ids. */
+int ds2i_gpu_batch_fetch_docids(ds2i_gpu_batch*, uint32_t* out_docids);
 /* Device-side counters of the last run: [0] docs blocks decoded, [1] freqs blocks decoded,
  * [2] compressed docs bytes, [3] compressed freqs bytes, [4] block_max entries read,
  * [5] documents scored, [6] kernel launches.  These are the algorithmic bytes of SURVEY.md §8(d). */
@@ -106,6 +120,14 @@ int ds2i_gpu_batch_stats(ds2i_gpu_batch*, uint64_t out_stats[8]);
 /* Device addresses of the last run's results (counts: nq u64; scores: nq*k f32), for callers that
  * hand them to a collective (NCCL gather of per-shard top-k) without a host round trip. */
 int ds2i_gpu_batch_device_results(ds2i_gpu_batch*, void** d_counts, void** d_scores);
+int ds2i_gpu_batch_device_docids(ds2i_gpu_batch*, void** d_docids);      /* device pointer to the nq * k docids of the last ranked run */
+
+/* Document-partitioned shards.  Every shard evaluated the same nq queries; row (s * nq + q) of the
+ * DEVICE arrays d_counts / d_scores / d_docids (docids already global) holds shard s's result for query q — the layout an
+ * NCCL all_gather of the per-shard results produces.  Shards hold disjoint documents: unranked counts add up, the
+ * global top-k is the top-k of the shards' lists.  Outputs are device arrays (nq, nq * k, nq * k). */
+int ds2i_gpu_merge_shards(const uint64_t* d_counts, const float* d_scores, const uint32_t* d_docids, uint32_t nshards, size_t nq,
+                          uint32_t k, int ranked, uint64_t* d_out_counts, float* d_out_scores, uint32_t* d_out_docids);
 void ds2i_gpu_batch_free(ds2i_gpu_batch*);
 
 /* ---- Enumerator-level entry points (document_enumerator, block_posting_list.hpp:105-186) -------

@@ -65,11 +65,16 @@ private:
 struct query_batch_result {
     std::vector<uint64_t> counts;                    // the operator's return value per query
     std::vector<float> scores;                       // nq * k, descending, zero padded
+    std::vector<uint32_t> docids;                    // nq * k: the document of every score (ranked operators)
     uint32_t k = 0;
     float elapsed_ms = 0;                            // CUDA-event time of the device work
     std::vector<float> topk(size_t q) const {
         size_t n = size_t(counts[q] < k ? counts[q] : k);
         return std::vector<float>(scores.begin() + q * k, scores.begin() + q * k + n);
+    }
+    std::vector<uint32_t> topk_docids(size_t q) const {
+        size_t n = size_t(counts[q] < k ? counts[q] : k);
+        return std::vector<uint32_t>(docids.begin() + q * k, docids.begin() + q * k + n);
     }
     double qps() const { return elapsed_ms > 0 ? counts.size() / (elapsed_ms * 1e-3) : 0; }
 };
@@ -86,8 +91,9 @@ inline query_batch_result run_batch(gpu_index const& index, gpu_wand_data const*
     r.k = k;
     r.counts.resize(queries.size());
     r.scores.assign(queries.size() * k, 0.f);
-    check(ds2i_gpu_query_batch(index.handle(), wdata ? wdata->handle() : nullptr, op, k, terms.data(), offsets.data(), queries.size(),
-                               r.counts.data(), r.scores.data(), &r.elapsed_ms));
+    r.docids.assign(queries.size() * k, 0xffffffffu);
+    check(ds2i_gpu_query_batch_docids(index.handle(), wdata ? wdata->handle() : nullptr, op, k, terms.data(), offsets.data(), queries.size(),
+                                      r.counts.data(), r.scores.data(), r.docids.data(), &r.elapsed_ms));
     return r;
 }
 
@@ -107,14 +113,16 @@ public:
     uint64_t operator()(gpu_index const& index, term_id_vec const& terms) {
         std::vector<term_id_vec> one(1, terms);
         query_batch_result r = run_batch(index, m_wdata, OP, one, m_k);
-        if (RANKED) m_topk = r.topk(0);
+        if (RANKED) { m_topk = r.topk(0); m_topk_docids = r.topk_docids(0); }
         return r.counts[0];
     }
     std::vector<float> const& topk() const { return m_topk; }
+    std::vector<uint32_t> const& topk_docids() const { return m_topk_docids; }     // extension: the reference keeps scores only
 private:
     gpu_wand_data const* m_wdata;
     uint32_t m_k;
     std::vector<float> m_topk;
+    std::vector<uint32_t> m_topk_docids;
 };
 
 typedef gpu_query_operator<DS2I_OP_AND, false> gpu_and_query;
