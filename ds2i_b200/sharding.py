@@ -41,18 +41,9 @@ class Shard:
         self._lookup = None
 
     def map_queries(self, queries, op):
-        """Global term ids -> list numbers of this shard.  A term without postings here has no list (ds2i lists cannot
-        be empty): a conjunctive query then matches nothing in this shard, a disjunctive one just loses the term."""
         if getattr(self, "_lookup", None) is None:
             self._lookup = {int(t): i for i, t in enumerate(self.terms)}
-        out = []
-        for q in queries:
-            local = [self._lookup.get(int(t), -1) for t in q]
-            if op in CONJUNCTIVE and any(t < 0 for t in local):
-                out.append([])
-            else:
-                out.append([t for t in local if t >= 0])
-        return out
+        return map_queries(self._lookup, queries, op)
 
     def run(self, op, queries, k):
         """-> (counts [nq] i64, scores [nq,k] f32, docids [nq,k] i64, global) as torch CUDA tensors owned by the caller."""
@@ -70,6 +61,20 @@ class Shard:
                    torch.full((len(queries), k), 0xFFFFFFFF, dtype=torch.int64, device=c.device))
         batch.close()
         return res
+
+
+def map_queries(lookup, queries, op):
+    """Global term ids -> list numbers of a shard (`lookup`: global id -> local list).  A term without postings in the
+    shard has no list (ds2i lists cannot be empty): a conjunctive query then matches nothing there, a disjunctive one
+    just loses the term."""
+    out = []
+    for q in queries:
+        local = [lookup.get(int(t), -1) for t in q]
+        if op in CONJUNCTIVE and any(t < 0 for t in local):
+            out.append([])
+        else:
+            out.append([t for t in local if t >= 0])
+    return out
 
 
 def shard_ranges(num_docs_total, num_shards):
@@ -117,6 +122,17 @@ def merge_shard_results(counts, scores, docids, k, ranked):
     return oc, os_, od.to(torch.int64) & 0xFFFFFFFF
 
 
+def gather_shard_rows(t, world):
+    """[S_local, ...] on every rank -> [world * S_local, ...], rank-major: the row layout ds2i_gpu_merge_shards reads."""
+    if world == 1:
+        return t
+    import torch
+    import torch.distributed as dist
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+    return out.view((world * t.shape[0],) + tuple(t.shape[1:]))
+
+
 def query_sharded(shards, op, queries, k=10, world=1):
     """Evaluate `queries` on the shards of this process, gather the other ranks' results when world > 1 (every rank
     ends up with the merged answer), merge on the device.  -> numpy (counts, scores, docids)."""
@@ -125,12 +141,6 @@ def query_sharded(shards, op, queries, k=10, world=1):
     counts = torch.stack([r[0] for r in res])
     scores = torch.stack([r[1] for r in res])
     docids = torch.stack([r[2] for r in res])
-    if world > 1:
-        import torch.distributed as dist
-        def gather(t):
-            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
-            return out.view((world * t.shape[0],) + tuple(t.shape[1:]))
-        counts, scores, docids = gather(counts), gather(scores), gather(docids)
+    counts, scores, docids = gather_shard_rows(counts, world), gather_shard_rows(scores, world), gather_shard_rows(docids, world)
     oc, os_, od = merge_shard_results(counts, scores, docids, k, op in RANKED)
     return oc.cpu().numpy().astype(np.uint64), os_.cpu().numpy(), od.cpu().numpy().astype(np.uint32)

@@ -8,7 +8,7 @@
  * the GPU box has a checker even if those binaries could not run there, and as an independent
  * reading of the formats.  PINNED: tests/test_oracle.py checks it bit-for-bit against the golden
  * vectors the reference itself produced (tests/golden/mini.expected.strict.bin, mini.collection.npz)
- * for every operator and every posting, for block_optpfor, block_interpolative and block_varint.
+ * for every operator and every posting, for block_optpfor, block_interpolative, block_varint and block_mixed.
  * Not restated here (the compiled reference is their only oracle): QMX, partitioned Elias-Fano.
  *
  *   ds2i_oracle dump  <type> <index> <wand> <queries> <out.bin> <op[:op..]> [k]
@@ -24,7 +24,7 @@
 #include <string.h>
 #include <time.h>
 
-enum { OPTPFOR, VARINT, INTERPOLATIVE };
+enum { OPTPFOR, VARINT, INTERPOLATIVE, MIXED };
 
 /* ---- succinct::mapper layout (succinct/mapper.hpp:51-98), block_freq_index::map (block_freq_index.hpp:124-134) */
 typedef struct {
@@ -83,6 +83,7 @@ static int open_index(block_index* ix, const char* type, const uint8_t* p) {
     if (!strcmp(type, "block_optpfor")) ix->codec = OPTPFOR;
     else if (!strcmp(type, "block_varint")) ix->codec = VARINT;
     else if (!strcmp(type, "block_interpolative")) ix->codec = INTERPOLATIVE;
+    else if (!strcmp(type, "block_mixed")) ix->codec = MIXED;
     else return -1;
     const uint8_t* c = p + 8;                /* flags */
     unsigned ls0 = c[0], ls1 = c[1]; c += 5; /* global_parameters: 5 single bytes */
@@ -203,6 +204,11 @@ static const uint8_t* varint_decode(const uint8_t* in, uint32_t* out, size_t n) 
 }
 static const uint8_t* block_decode(int codec, const uint8_t* in, uint32_t* out, uint32_t sum, size_t n) {
     if (codec == INTERPOLATIVE || n < 128) return interpolative_decode(in, out, sum, n);   /* block_codecs.hpp:196-199,215-217 */
+    if (codec == MIXED) {       /* mixed_block::decode, mixed_block.hpp:198-217: block_type byte (pfor 0, varint 1, interpolative 2) */
+        int type = *in++;
+        if (type == 2) return interpolative_decode(in, out, sum, n);
+        codec = type == 0 ? OPTPFOR : VARINT;
+    }
     return codec == OPTPFOR ? optpfor_decode(in, out) : varint_decode(in, out, n);
 }
 

@@ -41,3 +41,62 @@ def test_gather_topk_world_size_2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+# ---- document-partitioned shards (ds2i_b200/sharding.py): the host-side logic, without a GPU ----------------------
+def test_shard_ranges_and_term_mapping():
+    from ds2i_b200.sharding import map_queries, shard_ranges
+    assert shard_ranges(10, 3) == [(0, 3), (3, 6), (6, 10)]
+    lookup = {5: 0, 9: 1}                                   # this shard holds lists for the global terms 5 and 9
+    qs = [[5, 9], [5, 7], [7], []]
+    assert map_queries(lookup, qs, "ranked_and") == [[0, 1], [], [], []]      # a missing term empties a conjunction
+    assert map_queries(lookup, qs, "wand") == [[0, 1], [0], [], []]           # ... and just drops out of a disjunction
+    assert map_queries(lookup, qs, "or") == [[0, 1], [0], [], []]
+
+
+class _FakeIndex:
+    def __init__(self, n):
+        self.n = n
+
+    def num_docs(self):
+        return self.n
+
+
+class _FakeShard:
+    """what exchange_global_stats needs of a Shard"""
+
+    def __init__(self, terms, sizes, ndocs):
+        import numpy as np
+        self.terms, self.sizes, self.index, self.got = np.asarray(terms), np.asarray(sizes), _FakeIndex(ndocs), None
+
+    def local_df(self, num_terms_global):
+        import numpy as np
+        df = np.zeros(num_terms_global, dtype=np.int64)
+        df[self.terms] = self.sizes
+        return df
+
+    def set_global_stats(self, df, ndocs):
+        self.got = (df.copy(), ndocs)
+
+
+def _stats_worker(rank, world, port, out):
+    import numpy as np
+    from ds2i_b200.sharding import exchange_global_stats, gather_shard_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = _FakeShard([0, 2] if rank == 0 else [1, 2], [3, 4] if rank == 0 else [5, 6], 100 + rank)
+    df, ndocs = exchange_global_stats([sh], 4, world)
+    ok = ndocs == 201 and df.tolist() == [3, 5, 10, 0] and sh.got[1] == 201 and sh.got[0].tolist() == [3, 5, 10, 0]
+    rows = gather_shard_rows(torch.full((1, 2, 3), float(rank)), world)       # [S_local=1, nq=2, k=3] per rank
+    ok = ok and rows.shape == (world, 2, 3) and all(bool((rows[r] == r).all()) for r in range(world))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_global_stats_exchange_world_size_2_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_stats_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
