@@ -9,7 +9,9 @@
  * reading of the formats.  PINNED: tests/test_oracle.py checks it bit-for-bit against the golden
  * vectors the reference itself produced (tests/golden/mini.expected.strict.bin, mini.collection.npz)
  * for every operator and every posting, for block_optpfor, block_interpolative, block_varint and block_mixed.
- * Not restated here (the compiled reference is their only oracle): QMX, partitioned Elias-Fano.
+ * The Elias-Fano family (opt, uniform, single, ef) is restated as a full decode of every list (formats, partition
+ * encodings, strict / positive transformations); the operators then run over the decoded arrays.
+ * Not restated here (the compiled reference is its only oracle): QMX.
  *
  *   ds2i_oracle dump  <type> <index> <wand> <queries> <out.bin> <op[:op..]> [k]
  *   ds2i_oracle lists <type> <index> <out.bin>            every posting of every list
@@ -53,12 +55,12 @@ static uint64_t bv_bits(const uint8_t* words, uint64_t pos, unsigned len) {   /*
 static unsigned msb64(uint64_t x) { return 63 - (unsigned)__builtin_clzll(x); }
 static uint64_t ceil_log2(uint64_t x) { return x > 1 ? msb64(x - 1) + 1 : 0; }   /* util.hpp:30-33 */
 
-/* compact_elias_fano (compact_elias_fano.hpp:14-61,105-118): all n values of the sequence */
-static void ef_decode_all(const uint8_t* words, uint64_t universe, uint64_t n, unsigned ls0, unsigned ls1, uint64_t* out) {
+/* compact_elias_fano (compact_elias_fano.hpp:14-61,105-118): all n values of the sequence written at bit `off` */
+static void ef_decode_at(const uint8_t* words, uint64_t off, uint64_t universe, uint64_t n, unsigned ls0, unsigned ls1, uint64_t* out) {
     uint64_t l = universe > n ? msb64(universe / n) : 0;
     uint64_t hbl = n + (universe >> l) + 2, psize = ceil_log2(hbl);
-    uint64_t p0 = (hbl - n) >> ls0, p1 = n >> ls1;
-    uint64_t high_off = p0 * psize + p1 * psize, low_off = high_off + hbl;
+    uint64_t p0 = ls0 >= 63 ? 0 : (hbl - n) >> ls0, p1 = n >> ls1;
+    uint64_t high_off = off + p0 * psize + p1 * psize, low_off = high_off + hbl;
     uint64_t pos = high_off;
     for (uint64_t i = 0; i < n; ++i) {
         while (!bv_bits(words, pos, 1)) ++pos;
@@ -66,6 +68,16 @@ static void ef_decode_all(const uint8_t* words, uint64_t universe, uint64_t n, u
         out[i] = (high << l) | bv_bits(words, low_off + i * l, (unsigned)l);
         ++pos;
     }
+}
+static void ef_decode_all(const uint8_t* words, uint64_t universe, uint64_t n, unsigned ls0, unsigned ls1, uint64_t* out) {
+    ef_decode_at(words, 0, universe, n, ls0, ls1, out);
+}
+/* bits the sequence occupies (compact_elias_fano.hpp:14-61 `end`) */
+static uint64_t ef_bitsize(uint64_t universe, uint64_t n, unsigned ls0, unsigned ls1) {
+    uint64_t l = universe > n ? msb64(universe / n) : 0;
+    uint64_t hbl = n + (universe >> l) + 2, psize = ceil_log2(hbl);
+    uint64_t p0 = ls0 >= 63 ? 0 : (hbl - n) >> ls0, p1 = n >> ls1;
+    return p0 * psize + p1 * psize + hbl + n * l;
 }
 
 static int load_file(const char* path, uint8_t** data, size_t* n) {
@@ -212,6 +224,134 @@ static const uint8_t* block_decode(int codec, const uint8_t* in, uint32_t* out, 
     return codec == OPTPFOR ? optpfor_decode(in, out) : varint_decode(in, out, n);
 }
 
+/* ==== freq_index family: ef / single / uniform / opt (index_types.hpp:18-35) =========================================
+ * Full decode of a list's docs and freqs sequences; the query operators below then run over the decoded arrays.  What is
+ * restated is the READING of the formats (headers, partitions, the three partition encodings, the strict / positive
+ * transformations), not the reference's skipping machinery (pointers, rank samples), which never changes a value. */
+enum { V_OPT, V_UNIFORM, V_SINGLE, V_EF };
+typedef struct {
+    int variant;
+    uint64_t size, num_docs;
+    unsigned ls0, ls1, rb0, rb1, logp;           /* global_parameters (global_parameters.hpp:6-20) */
+    const uint8_t *dwords, *fwords;              /* m_bitvectors of the two bitvector_collections */
+    uint64_t dbits, fbits;
+    uint64_t *dstart, *fstart;                   /* decoded m_endpoints (bitvector_collection.hpp:57-67) */
+} ef_index;
+static const ef_index* g_ef = 0;                 /* set: enumerators are backed by fully decoded EF-family lists */
+
+typedef struct { const uint8_t* w; uint64_t pos; } bit_cursor;
+static uint64_t bc_take(bit_cursor* c, unsigned len) { uint64_t v = bv_bits(c->w, c->pos, len); c->pos += len; return v; }
+static uint64_t bc_gamma(bit_cursor* c) {        /* integer_codes.hpp:21-25 */
+    unsigned l = 0;
+    while (!bv_bits(c->w, c->pos, 1)) { ++c->pos; ++l; }
+    ++c->pos;
+    return (bc_take(c, l) | ((uint64_t)1 << l)) - 1;
+}
+static uint64_t bc_delta(bit_cursor* c) { uint64_t l = bc_gamma(c); return (bc_take(c, (unsigned)l) | ((uint64_t)1 << l)) - 1; }   /* :41-45 */
+
+/* one indexed_sequence / strict_sequence (indexed_sequence.hpp:89-127, strict_sequence.hpp:50-137) or, raw, one
+ * compact_elias_fano / strict_elias_fano (ef_index): n values in [0, universe) */
+static void base_decode(const ef_index* ix, const uint8_t* w, uint64_t off, uint64_t universe, uint64_t n, int strict, uint64_t* out) {
+    if (ix->variant == V_EF) {                   /* strict_elias_fano.hpp:20-36: v - i over universe - n + 1, global sampling */
+        ef_decode_at(w, off, strict ? universe - n + 1 : universe, n, ix->ls0, ix->ls1, out);
+        if (strict) for (uint64_t i = 0; i < n; ++i) out[i] += i;
+        return;
+    }
+    if (universe == n) { for (uint64_t i = 0; i < n; ++i) out[i] = i; return; }      /* all_ones_sequence.hpp:25-75, no type bit */
+    int type = (int)bv_bits(w, off, 1);
+    off += 1;
+    if (type == 0) {                             /* elias_fano; the strict variants never index zeros (strict_sequence.hpp:24-30) */
+        ef_decode_at(w, off, strict ? universe - n + 1 : universe, n, strict ? 63 : ix->ls0, ix->ls1, out);
+        if (strict) for (uint64_t i = 0; i < n; ++i) out[i] += i;
+    } else {                                     /* compact_ranked_bitvector.hpp:14-50: rank samples | select pointers | bitmap */
+        unsigned rs0 = strict ? 63 : ix->rb0;
+        uint64_t samples = rs0 >= 63 ? 0 : universe >> rs0, p1 = n >> ix->rb1;
+        uint64_t bits_off = off + samples * ceil_log2(n + 1) + p1 * ceil_log2(universe);
+        uint64_t k = 0;
+        for (uint64_t v = 0; v < universe && k < n; ++v)
+            if (bv_bits(w, bits_off + v, 1)) out[k++] = v;
+    }
+}
+
+/* partitioned_sequence (partitioned_sequence.hpp:21-178) / uniform_partitioned_sequence (uniform_partitioned_sequence.hpp:19-160) */
+static void sequence_decode(const ef_index* ix, const uint8_t* w, uint64_t off, uint64_t universe, uint64_t n, int strict, uint64_t* out) {
+    if (ix->variant == V_SINGLE || ix->variant == V_EF) { base_decode(ix, w, off, universe, n, strict, out); return; }
+    bit_cursor it = {w, off};
+    uint64_t partitions = bc_gamma(&it) + 1;
+    if (partitions == 1) {
+        uint64_t base = bc_take(&it, (unsigned)ceil_log2(universe)), ub = 0;
+        if (n > 1) { uint64_t d = bc_delta(&it); ub = d ? d : universe - base - 1; }
+        base_decode(ix, w, it.pos, ub + 1, n, strict, out);
+        for (uint64_t i = 0; i < n; ++i) out[i] += base;
+        return;
+    }
+    uint64_t endpoint_bits = bc_gamma(&it);
+    uint64_t cur = it.pos;
+    uint64_t* sizes = 0;
+    if (ix->variant == V_OPT) {                  /* cumulative partition sizes: EF over n, partitions - 1 values */
+        sizes = (uint64_t*)malloc(8 * partitions);
+        ef_decode_at(w, cur, n, partitions - 1, ix->ls0, ix->ls1, sizes);
+        cur += ef_bitsize(n, partitions - 1, ix->ls0, ix->ls1);
+    }
+    uint64_t* ubs = (uint64_t*)malloc(8 * (partitions + 1));
+    ef_decode_at(w, cur, universe, partitions + 1, ix->ls0, ix->ls1, ubs);      /* first value, then every partition's last value */
+    cur += ef_bitsize(universe, partitions + 1, ix->ls0, ix->ls1);
+    uint64_t endpoints_off = cur, sequences_off = cur + endpoint_bits * (partitions - 1);
+    uint64_t psize = (uint64_t)1 << ix->logp;
+    for (uint64_t p = 0; p < partitions; ++p) {
+        uint64_t endpoint = p ? bv_bits(w, endpoints_off + (p - 1) * endpoint_bits, (unsigned)endpoint_bits) : 0;
+        uint64_t begin, end;
+        if (sizes) { begin = p ? sizes[p - 1] : 0; end = p + 1 < partitions ? sizes[p] : n; }
+        else { begin = p * psize; end = (p + 1) * psize < n ? (p + 1) * psize : n; }
+        uint64_t base = ubs[p] + (p ? 1 : 0), ub = ubs[p + 1];
+        base_decode(ix, w, sequences_off + endpoint, ub - base + 1, end - begin, strict, out + begin);
+        for (uint64_t i = begin; i < end; ++i) out[i] += base;
+    }
+    free(sizes); free(ubs);
+}
+
+/* freq_index::map (freq_index.hpp:234-243) over succinct::mapper's layout */
+static int open_ef_index(ef_index* ix, const char* type, const uint8_t* p) {
+    if (!strcmp(type, "opt")) ix->variant = V_OPT;
+    else if (!strcmp(type, "uniform")) ix->variant = V_UNIFORM;
+    else if (!strcmp(type, "single")) ix->variant = V_SINGLE;
+    else if (!strcmp(type, "ef")) ix->variant = V_EF;
+    else return -1;
+    const uint8_t* c = p + 8;
+    ix->ls0 = c[0]; ix->ls1 = c[1]; ix->rb0 = c[2]; ix->rb1 = c[3]; ix->logp = c[4]; c += 5;
+    ix->num_docs = rd64(c); c += 8;
+    for (int which = 0; which < 2; ++which) {
+        uint64_t size = rd64(c); c += 8;
+        uint64_t ep_bits = rd64(c), ep_nwords = rd64(c + 8); c += 16; (void)ep_bits;
+        const uint8_t* ep_words = c; c += 8 * ep_nwords;
+        uint64_t bits = rd64(c), nwords = rd64(c + 8); c += 16;
+        const uint8_t* words = c; c += 8 * nwords;
+        uint64_t* start = (uint64_t*)malloc(8 * (size + 1));
+        ef_decode_all(ep_words, bits, size, ix->ls0, ix->ls1, start);             /* bitvector_collection.hpp:40-46 */
+        ix->size = size;
+        if (which == 0) { ix->dwords = words; ix->dbits = bits; ix->dstart = start; }
+        else { ix->fwords = words; ix->fbits = bits; ix->fstart = start; }
+    }
+    return 0;
+}
+
+/* freq_index::operator[] (freq_index.hpp:192-214): gamma(occurrences), n, the docs sequence; freqs are the differences of
+ * a strict positive sequence over occurrences + 1 (positive_sequence.hpp:18-78) */
+static uint32_t ef_list_decode(const ef_index* ix, uint64_t term, uint32_t** docs_out, uint32_t** freqs_out) {
+    bit_cursor it = {ix->dwords, ix->dstart[term]};
+    uint64_t occurrences = bc_gamma(&it) + 1, n = 1;
+    if (occurrences > 1) n = bc_take(&it, (unsigned)ceil_log2(occurrences + 1));
+    uint64_t* tmp = (uint64_t*)malloc(8 * n);
+    uint32_t *docs = (uint32_t*)malloc(4 * n), *freqs = (uint32_t*)malloc(4 * n);
+    sequence_decode(ix, ix->dwords, it.pos, ix->num_docs, n, 0, tmp);
+    for (uint64_t i = 0; i < n; ++i) docs[i] = (uint32_t)tmp[i];
+    sequence_decode(ix, ix->fwords, ix->fstart[term], occurrences + 1, n, 1, tmp);
+    for (uint64_t i = 0; i < n; ++i) freqs[i] = (uint32_t)(tmp[i] - (i ? tmp[i - 1] : 0));
+    free(tmp);
+    *docs_out = docs; *freqs_out = freqs;
+    return (uint32_t)n;
+}
+
 /* ---- block_posting_list::document_enumerator (block_posting_list.hpp:84-355) ---- */
 typedef struct {
     int codec;
@@ -222,6 +362,7 @@ typedef struct {
     const uint8_t* freqs_block_data;
     int freqs_decoded;
     uint32_t docs_buf[128], freqs_buf[128];
+    uint32_t *adocs, *afreqs, apos;      /* EF family: the whole list, decoded (adocs != 0) */
 } enumerator;
 
 static uint32_t block_max(const enumerator* e, uint32_t b) { return rd32(e->block_maxs + 4 * (size_t)b); }
@@ -236,6 +377,12 @@ static void decode_docs_block(enumerator* e, uint64_t block) {   /* :292-319 */
     e->cur_block = (uint32_t)block; e->pos_in_block = 0; e->cur_docid = e->docs_buf[0]; e->freqs_decoded = 0;
 }
 static void enum_open(enumerator* e, const block_index* ix, uint64_t term) {   /* :86-108; block_freq_index.hpp:85-94 */
+    if (g_ef) {
+        free(e->adocs); free(e->afreqs);
+        e->n = ef_list_decode(g_ef, term, &e->adocs, &e->afreqs);
+        e->universe = g_ef->num_docs; e->apos = 0; e->cur_docid = e->adocs[0];
+        return;
+    }
     const uint8_t* data = ix->lists + ix->list_start[term];
     e->codec = ix->codec;
     e->block_maxs = vbyte_decode(data, &e->n);
@@ -246,6 +393,7 @@ static void enum_open(enumerator* e, const block_index* ix, uint64_t term) {   /
     decode_docs_block(e, 0);
 }
 static void enum_next(enumerator* e) {   /* :110-122 */
+    if (e->adocs) { ++e->apos; e->cur_docid = e->apos < e->n ? e->adocs[e->apos] : (uint32_t)e->universe; return; }
     ++e->pos_in_block;
     if (e->pos_in_block == e->cur_block_size) {
         if (e->cur_block + 1 == e->blocks) { e->cur_docid = (uint32_t)e->universe; return; }
@@ -253,6 +401,11 @@ static void enum_next(enumerator* e) {   /* :110-122 */
     } else e->cur_docid += e->docs_buf[e->pos_in_block] + 1;
 }
 static void enum_next_geq(enumerator* e, uint64_t lower_bound) {   /* :124-146 */
+    if (e->adocs) {     /* first posting >= lower_bound at or after the cursor (the operators never ask for less) */
+        while (e->apos < e->n && e->adocs[e->apos] < lower_bound) ++e->apos;
+        e->cur_docid = e->apos < e->n ? e->adocs[e->apos] : (uint32_t)e->universe;
+        return;
+    }
     if (lower_bound > e->cur_block_max) {
         if (lower_bound > block_max(e, e->blocks - 1)) { e->cur_docid = (uint32_t)e->universe; return; }
         uint64_t block = e->cur_block + 1;
@@ -262,6 +415,7 @@ static void enum_next_geq(enumerator* e, uint64_t lower_bound) {   /* :124-146 *
     while (e->cur_docid < lower_bound) e->cur_docid += e->docs_buf[++e->pos_in_block] + 1;
 }
 static uint64_t enum_freq(enumerator* e) {   /* :165-171,321-331 */
+    if (e->adocs) return e->afreqs[e->apos];
     if (!e->freqs_decoded) {
         block_decode(e->codec, e->freqs_block_data, e->freqs_buf, (uint32_t)-1, e->cur_block_size);
         e->freqs_decoded = 1;
@@ -499,7 +653,13 @@ int main(int argc, char** argv) {
     uint8_t* ibytes; size_t in;
     if (load_file(argv[3], &ibytes, &in)) { perror(argv[3]); return 1; }
     block_index ix;
-    if (open_index(&ix, argv[2], ibytes)) { fprintf(stderr, "unsupported index type %s\n", argv[2]); return 1; }
+    static ef_index efx;
+    if (open_index(&ix, argv[2], ibytes)) {
+        if (open_ef_index(&efx, argv[2], ibytes)) { fprintf(stderr, "unsupported index type %s\n", argv[2]); return 1; }
+        g_ef = &efx;
+        memset(&ix, 0, sizeof ix);
+        ix.size = efx.size; ix.num_docs = efx.num_docs;
+    }
     if (!strcmp(argv[1], "lists")) {
         FILE* f = fopen(argv[4], "wb");
         static enumerator e;
