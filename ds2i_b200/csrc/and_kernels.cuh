@@ -97,7 +97,7 @@ __device__ __forceinline__ uint32_t and_stage(const uint8_t* lists, uint64_t sta
     return uint32_t(start - a0);
 }
 
-template <int CODEC>
+template <int CODEC, bool WIDE_EXC = false>
 __device__ __forceinline__ uint32_t and_decode_values(uint32_t stage_off, uint32_t off, uint32_t size, uint32_t sum_of_values, uint32_t out_off,
                                                       uint32_t stack_off, bool& prefix_out) {
     if (CODEC == CODEC_MIXED && size == BLOCK) {
@@ -105,12 +105,12 @@ __device__ __forceinline__ uint32_t and_decode_values(uint32_t stage_off, uint32
         const uint32_t type = lds_u8(smem_words(stage_off), off);
         prefix_out = type == 2u;
         if (type == 1u) return 1u + decode_varint128(stage_off, off + 1u, out_off);
-        if (type == 0u) return 1u + decode_optpfor128(stage_off, off + 1u, out_off, stack_off);
+        if (type == 0u) return 1u + decode_optpfor128<WIDE_EXC>(stage_off, off + 1u, out_off, stack_off);
         return 1u + decode_interpolative_prefix(stage_off, off + 1u, size, sum_of_values, out_off, stack_off);
     }
     if (CODEC != CODEC_INTERPOLATIVE && CODEC != CODEC_MIXED && size == BLOCK) {
         prefix_out = false;
-        if (CODEC == CODEC_OPTPFOR) return decode_optpfor128(stage_off, off, out_off, stack_off);
+        if (CODEC == CODEC_OPTPFOR) return decode_optpfor128<WIDE_EXC>(stage_off, off, out_off, stack_off);
         if (CODEC == CODEC_VARINT) return decode_varint128(stage_off, off, out_off);
         return decode_qmx128(stage_off, off, out_off);
     }

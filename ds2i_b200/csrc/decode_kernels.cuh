@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(128, 8) decode_full_blocks_kernel(DevIndex idx
                 if (CODEC == CODEC_INTERPOLATIVE || (b + 1u) * BLOCK > d.n) continue;      // bit-serial blocks: the other kernel
                 const uint32_t off = and_stage(idx.lists, data_off + e0, data_off + e1, stage, bar, phase);
                 bool dprefix, fprefix;
-                const uint32_t consumed = and_decode_values<CODEC>(stage_off, off, BLOCK, cur_max - prev_max - BLOCK, docs_off, stack_off, dprefix);
-                and_decode_values<CODEC>(stage_off, off + consumed, BLOCK, 0xffffffffu, freqs_off, stack_off, fprefix);
+                const uint32_t consumed = and_decode_values<CODEC, true>(stage_off, off, BLOCK, cur_max - prev_max - BLOCK, docs_off, stack_off, dprefix);
+                and_decode_values<CODEC, true>(stage_off, off + consumed, BLOCK, 0xffffffffu, freqs_off, stack_off, fprefix);
                 uint32_t* od = job.out_docs + out_base + uint64_t(b) * BLOCK + lane;
                 uint32_t* of = job.out_freqs + out_base + uint64_t(b) * BLOCK + lane;
                 if (!dprefix) {
