@@ -8,10 +8,9 @@
  * the GPU box has a checker even if those binaries could not run there, and as an independent
  * reading of the formats.  PINNED: tests/test_oracle.py checks it bit-for-bit against the golden
  * vectors the reference itself produced (tests/golden/mini.expected.strict.bin, mini.collection.npz)
- * for every operator and every posting, for block_optpfor, block_interpolative, block_varint and block_mixed.
+ * for every operator and every posting, for all nine index types of DS2I_INDEX_TYPES.
  * The Elias-Fano family (opt, uniform, single, ef) is restated as a full decode of every list (formats, partition
  * encodings, strict / positive transformations); the operators then run over the decoded arrays.
- * Not restated here (the compiled reference is its only oracle): QMX.
  *
  *   ds2i_oracle dump  <type> <index> <wand> <queries> <out.bin> <op[:op..]> [k]
  *   ds2i_oracle lists <type> <index> <out.bin>            every posting of every list
@@ -26,7 +25,7 @@
 #include <string.h>
 #include <time.h>
 
-enum { OPTPFOR, VARINT, INTERPOLATIVE, MIXED };
+enum { OPTPFOR, VARINT, INTERPOLATIVE, MIXED, QMX };
 
 /* ---- succinct::mapper layout (succinct/mapper.hpp:51-98), block_freq_index::map (block_freq_index.hpp:124-134) */
 typedef struct {
@@ -96,6 +95,7 @@ static int open_index(block_index* ix, const char* type, const uint8_t* p) {
     else if (!strcmp(type, "block_varint")) ix->codec = VARINT;
     else if (!strcmp(type, "block_interpolative")) ix->codec = INTERPOLATIVE;
     else if (!strcmp(type, "block_mixed")) ix->codec = MIXED;
+    else if (!strcmp(type, "block_qmx")) ix->codec = QMX;
     else return -1;
     const uint8_t* c = p + 8;                /* flags */
     unsigned ls0 = c[0], ls1 = c[1]; c += 5; /* global_parameters: 5 single bytes */
@@ -214,6 +214,49 @@ static const uint8_t* varint_decode(const uint8_t* in, uint32_t* out, size_t n) 
     }
     return in;
 }
+/* qmx_block::decode (block_codecs.hpp:336-349) over QMX::codec<128>::decode (qmx_codec.hpp:636-6115), scalar.
+ * TightVByte(len), then len bytes: payload stripes from the front, key bytes from the back (consumed in reverse while the
+ * payload cursor has not passed them, :655-656).  key = type << 4 | (16 - run).  A 128-bit stripe is four interleaved u32
+ * lanes (value v in lane v & 3, row v >> 2); types 8 / 12 / 14 are plain 8 / 16 / 32-bit arrays; the 7-, 9-, 12- and 21-bit
+ * types straddle a (lo, hi) stripe pair (:4833-4856, :5310-5338, :5700-5724, :5980-5998).  Only the first 128 values of
+ * the block are kept (the codec may overshoot, block_codecs.hpp:319). */
+static const uint8_t* qmx_decode(const uint8_t* in, uint32_t* out) {
+    static const uint16_t COUNT[16] = {256, 128, 64, 40, 32, 24, 20, 36, 16, 28, 12, 20, 8, 12, 4, 0};
+    static const uint8_t WIDTH[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 21, 32, 0};
+    uint32_t len;
+    in = vbyte_decode(in, &len);
+    uint32_t p = 0, o = 0;
+    for (uint32_t t = 0; t < len && o < 128; ++t) {
+        if (p > len - 1 - t) break;                       /* the payload cursor has passed the key */
+        uint32_t key = in[len - 1 - t], type = key >> 4, run = 16 - (key & 15);
+        int wide = type == 7 || type == 9 || type == 11 || type == 13;
+        uint32_t ub = type == 0 ? 0 : type == 15 ? 1 : wide ? 32 : 16, w = WIDTH[type];
+        for (uint32_t r = 0; r < run; ++r) {
+            const uint8_t* a = in + p + r * ub;
+            for (uint32_t v = 0; v < COUNT[type]; ++v, ++o) {
+                uint32_t val;
+                if (type == 0) val = 1;                   /* "0 bits" decodes to 1 (:129-133,657-660) */
+                else if (type == 8) val = a[v];
+                else if (type == 12) val = rd32(a + 2 * v) & 0xffff;
+                else if (type == 14) val = rd32(a + 4 * v);
+                else {
+                    uint32_t l = v & 3, row = v >> 2, mask = ((uint32_t)1 << w) - 1, lo = rd32(a + 4 * l);
+                    if (wide) {
+                        uint32_t hi = rd32(a + 16 + 4 * l), rs = 32 / w;
+                        uint32_t resume = type == 7 ? 3 : type == 9 ? 4 : type == 11 ? 8 : 11;
+                        if (row < rs) val = (lo >> (row * w)) & mask;
+                        else if (row == rs) val = ((lo >> (rs * w)) | (hi << (32 - rs * w))) & mask;
+                        else val = (hi >> (resume + w * (row - rs - 1))) & mask;
+                    } else val = (lo >> (row * w)) & mask;
+                }
+                if (o < 128) out[o] = val;
+            }
+        }
+        p += run * ub;
+    }
+    return in + len;
+}
+
 static const uint8_t* block_decode(int codec, const uint8_t* in, uint32_t* out, uint32_t sum, size_t n) {
     if (codec == INTERPOLATIVE || n < 128) return interpolative_decode(in, out, sum, n);   /* block_codecs.hpp:196-199,215-217 */
     if (codec == MIXED) {       /* mixed_block::decode, mixed_block.hpp:198-217: block_type byte (pfor 0, varint 1, interpolative 2) */
@@ -221,6 +264,7 @@ static const uint8_t* block_decode(int codec, const uint8_t* in, uint32_t* out, 
         if (type == 2) return interpolative_decode(in, out, sum, n);
         codec = type == 0 ? OPTPFOR : VARINT;
     }
+    if (codec == QMX) return qmx_decode(in, out);
     return codec == OPTPFOR ? optpfor_decode(in, out) : varint_decode(in, out, n);
 }
 
