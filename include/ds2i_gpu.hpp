@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ds2i_gpu.h"
@@ -29,6 +30,36 @@ inline void check(int rc) {
     throw std::runtime_error(msg);
 }
 
+// document_enumerator concept (block_posting_list.hpp:105-186, freq_index.hpp:116-190): the list is decoded ONCE on the
+// device (ds2i_gpu_decode_lists) and the cursor then walks the decoded postings on the host.  This is for code that steps
+// through single lists (verification, debugging, ad-hoc scans); the query operators never go through it — they evaluate
+// whole batches on the device.  Semantics kept from the reference: positioned on the first posting after construction;
+// past the end docid() == num_docs(); next_geq(lb) is "first posting >= lb at or after the cursor" (the block lists'
+// definition) and keeps returning num_docs() after the end; freq() is valid on a posting only.
+class gpu_document_enumerator {
+public:
+    gpu_document_enumerator() : m_pos(0), m_universe(0) {}
+    gpu_document_enumerator(std::vector<uint32_t> docs, std::vector<uint32_t> freqs, uint64_t universe)
+        : m_docs(std::move(docs)), m_freqs(std::move(freqs)), m_pos(0), m_universe(universe) {}
+    void reset() { m_pos = 0; }
+    void next() { if (m_pos < m_docs.size()) ++m_pos; }
+    void next_geq(uint64_t lower_bound) {
+        if (m_pos >= m_docs.size() || m_docs[m_pos] >= lower_bound) return;
+        size_t lo = m_pos + 1, hi = m_docs.size();        // first position in (m_pos, size) with docs >= lower_bound
+        while (lo < hi) { size_t mid = lo + (hi - lo) / 2; if (m_docs[mid] < lower_bound) lo = mid + 1; else hi = mid; }
+        m_pos = lo;
+    }
+    void move(uint64_t position) { m_pos = position < m_docs.size() ? size_t(position) : m_docs.size(); }
+    uint64_t docid() const { return m_pos < m_docs.size() ? m_docs[m_pos] : m_universe; }
+    uint64_t freq() const { return m_freqs[m_pos]; }
+    uint64_t position() const { return m_pos; }
+    uint64_t size() const { return m_docs.size(); }
+private:
+    std::vector<uint32_t> m_docs, m_freqs;
+    size_t m_pos;
+    uint64_t m_universe;
+};
+
 class gpu_index {                                    // models the Index concept (block_freq_index.hpp:73-134)
 public:
     gpu_index(const char* path, const char* index_type, int device = 0) : m_h(nullptr) {
@@ -43,6 +74,15 @@ public:
     size_t size() const { return size_t(ds2i_gpu_index_size(m_h)); }
     uint64_t num_docs() const { return ds2i_gpu_index_num_docs(m_h); }
     uint64_t list_size(term_id_type term) const { uint64_t n; check(ds2i_gpu_index_list_sizes(m_h, &term, 1, &n)); return n; }
+    typedef gpu_document_enumerator document_enumerator;
+    document_enumerator operator[](size_t term) const {       // Index::operator[] (block_freq_index.hpp:85-94, freq_index.hpp:192-214)
+        const uint32_t t = uint32_t(term);
+        uint64_t offsets[2] = {0, list_size(t)};
+        const size_t n = size_t(offsets[1]);
+        std::vector<uint32_t> docs(n), freqs(n);
+        check(ds2i_gpu_decode_lists(m_h, &t, 1, offsets, docs.data(), freqs.data(), nullptr));
+        return document_enumerator(std::move(docs), std::move(freqs), num_docs());
+    }
     void warmup(size_t) const {}                     // the index is resident in HBM
     ds2i_gpu_index* handle() const { return m_h; }
 private:

@@ -38,3 +38,14 @@ def test_no_cpu_fallback(native_lib):
     rc = native_lib.ds2i_gpu_index_open_file(os.path.join(GOLDEN, "mini.block_optpfor.idx").encode(), b"block_optpfor", 0, C.byref(h))
     assert rc == -3 and h.value is None        # DS2I_E_CUDA: fails loudly, nothing is computed on the CPU
     assert b"CUDA" in native_lib.ds2i_gpu_last_error() or b"cuda" in native_lib.ds2i_gpu_last_error()
+
+
+def test_cpp_adapters_compile_as_cpp11(native_lib, tmp_path):
+    """include/ds2i_gpu.hpp is what a ds2i maintainer includes (the reference builds with -std=c++11, CMakeLists.txt:9)."""
+    import subprocess
+    from ds2i_b200 import build
+    exe = tmp_path / "enumerator_walk"
+    r = subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                        os.path.join(ROOT, "tests", "cpp", "enumerator_walk.cpp"), "-L", build.LIBDIR, "-lds2i_gpu", "-Wl,-rpath," + build.LIBDIR],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
