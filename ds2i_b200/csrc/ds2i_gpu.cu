@@ -136,7 +136,7 @@ struct ds2i_gpu_batch {
     dev_buf<float> and_item_scores;
     size_t and_item_scores_k = 0;
     uint32_t n_and_items = 0, and_chunk = AND_CHUNK_BLOCKS;
-    // block-parallel union path (wand / maxscore): work items = (query, docid range)
+    // block-parallel union path (wand / maxscore): work items = (query, driving list, run of its blocks), implicit
     dev_buf<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_item_begin, un_item_sizes, un_threshold;
     dev_buf<float> un_item_scores, un_ub;
     size_t un_item_scores_k = 0;      // k the partial top-k buffer was sized for
