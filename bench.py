@@ -133,6 +133,22 @@ def run_reference_tool(paths, op, threads, sample, passes):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
+def reference_block_profile(paths, op, sample):
+    """Bytes the REFERENCE algorithm decodes per query: ds2i's own block_profiler (block_profiler.hpp:40-54,
+    what profile_queries.cpp uses) run over the first `sample` queries by oracle/_ref/ref_tool.  B_q = docs payload of the
+    blocks decoded at least once + freqs payload likewise + 8 B (block_max + endpoint) per decoded docs block."""
+    import numpy as np
+    tool = os.path.join(ROOT, "oracle", "_ref", "ref_tool")
+    out = os.path.join(os.path.dirname(paths["index"]), "profile.%s.bin" % op)
+    subprocess.run([tool, "profile", "block_optpfor", paths["index"], paths["wand"], paths["queries"], op, out, str(sample)],
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True, timeout=300)
+    raw = np.fromfile(out, dtype="<u8")
+    nq = int(raw[0])
+    a = raw[1:1 + 6 * nq].reshape(nq, 6).astype(np.float64)
+    return {"queries": nq, "docs_blocks_per_query": float(a[:, 0].mean()), "freqs_blocks_per_query": float(a[:, 1].mean()),
+            "bytes_per_query": float((a[:, 2] + a[:, 3] + 8 * a[:, 0]).mean()), "list_bytes_per_query": float(a[:, 4].mean())}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -325,6 +341,18 @@ def main():
                 out2 = run_reference_tool(paths, op2, cores, sample, 2)
                 line["also"][op2]["cpu_baseline"] = {"value": sample / out2["pass_seconds"][-1], "unit": "queries/s", "cores": cores, "kind": "reference",
                                                      "sample": "first %d queries, second of 2 passes, all host threads" % sample}
+            # the same roofline with the bytes the REFERENCE algorithm decodes (its own block_profiler) instead of the
+            # device counters: what SURVEY.md 8d defines as algorithmic bytes
+            try:
+                prof = reference_block_profile(paths, args.op, sample)
+                ref_bytes = prof["bytes_per_query"] * len(queries)
+                prof["achieved_GBps"] = ref_bytes / (kern_ms * 1e-3) / 1e9
+                prof["frac"] = prof["achieved_GBps"] / peak
+                prof["device_counted_bytes_per_query"] = alg_bytes / len(queries)
+                prof["sample"] = "block_profiler over the first %d queries, scaled to the %d of the step" % (prof["queries"], len(queries))
+                line["roofline"]["reference_block_profiler"] = prof
+            except Exception as e:
+                line["roofline"]["reference_block_profiler"] = {"failed": repr(e)}
             # parity at full size: the reference's own results for the first queries (the checker, not the product)
             ncheck = min(args.check, len(queries))
             if ncheck:
