@@ -8,7 +8,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_ranked_and.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:and_block_kernel -s 3 -c 1 -o $O/and_prof -f python bench.py --no-also --no-cpu-baseline --steps 1 --warmup 3 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:union_drive_kernel -s 3 -c 1 -o $O/union_prof -f python bench.py --op wand --no-also --no-cpu-baseline --steps 1 --warmup 3 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:decode_full_blocks_kernel -s 2 -c 1 -o $O/decode_prof -f python tools/microbench.py decode --steps 1 --warmup 1 > /dev/null 2>&1
+bash tools/prof_decode.sh
 python tools/microbench.py decode 2>/dev/null > $O/micro_decode.jsonl
 python tools/microbench.py pef 2>/dev/null > $O/micro_pef.jsonl
 cp ds2i_b200/lib/libds2i_gpu.so $O/libds2i_gpu.so.profiled
