@@ -692,6 +692,7 @@ static query_log read_queries(const char* path) {   /* read_query, queries.hpp:1
     return q;
 }
 
+#ifndef DS2I_ORACLE_NO_MAIN
 int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "usage: ds2i_oracle dump|lists|bench ...\n"); return 1; }
     uint8_t* ibytes; size_t in;
@@ -761,3 +762,4 @@ int main(int argc, char** argv) {
     fclose(f);
     return 0;
 }
+#endif
