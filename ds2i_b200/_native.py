@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libds2i_gpu.so")
+# DS2I_GPU_LIB selects another build of the same library (kernel experiments: tools/kbench.py)
+LIB_PATH = os.environ.get("DS2I_GPU_LIB") or os.path.join(_HERE, "lib", "libds2i_gpu.so")
 
 # every symbol include/ds2i_gpu.h declares
 SYMBOLS = [
@@ -15,6 +16,8 @@ SYMBOLS = [
     "ds2i_gpu_query_batch", "ds2i_gpu_query_batch_docids", "ds2i_gpu_batch_prepare", "ds2i_gpu_batch_run", "ds2i_gpu_batch_run_ex", "ds2i_gpu_batch_fetch", "ds2i_gpu_batch_fetch_docids",
     "ds2i_gpu_batch_stats", "ds2i_gpu_batch_device_results", "ds2i_gpu_batch_device_docids", "ds2i_gpu_merge_shards", "ds2i_gpu_batch_free",
     "ds2i_gpu_decode_lists", "ds2i_gpu_next_geq_batch",
+    "ds2i_gpu_decode_lists_checksum", "ds2i_gpu_index_type_known", "ds2i_gpu_batch_wait", "ds2i_gpu_batch_device_fused",
+    "ds2i_gpu_group_open", "ds2i_gpu_group_close", "ds2i_gpu_group_size", "ds2i_gpu_group_index", "ds2i_gpu_group_query_batch",
 ]
 
 _lib = None
@@ -64,6 +67,17 @@ def lib():
     L.ds2i_gpu_batch_free.restype = None
     L.ds2i_gpu_decode_lists.argtypes = [vp, u32p, C.c_size_t, u64p, u32p, u32p, f32p]
     L.ds2i_gpu_next_geq_batch.argtypes = [vp, u32p, C.c_size_t, u64p, u64p, u64p, u64p, f32p]
+    L.ds2i_gpu_decode_lists_checksum.argtypes = [vp, u32p, C.c_size_t, u64p, u64p, u64p, f32p]
+    L.ds2i_gpu_index_type_known.argtypes = [C.c_char_p]
+    L.ds2i_gpu_batch_wait.argtypes = [vp, f32p]
+    L.ds2i_gpu_batch_device_fused.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.ds2i_gpu_group_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.ds2i_gpu_group_close.argtypes = [vp]
+    L.ds2i_gpu_group_close.restype = None
+    L.ds2i_gpu_group_size.argtypes = [vp]
+    L.ds2i_gpu_group_index.argtypes = [vp, C.c_int]
+    L.ds2i_gpu_group_index.restype = vp
+    L.ds2i_gpu_group_query_batch.argtypes = [vp, C.c_int, C.c_uint32, u32p, u64p, C.c_size_t, u64p, f32p, u32p, f32p]
     _lib = L
     return L
 

@@ -36,6 +36,7 @@ class Index:
     def __init__(self, path, index_type, device=0):
         self._h = C.c_void_p()
         self.index_type = index_type
+        self.device = device
         L = _native.lib()
         _native.check(L.ds2i_gpu_index_open_file(str(path).encode(), index_type.encode(), device, C.byref(self._h)))
 
@@ -44,6 +45,7 @@ class Index:
         self = cls.__new__(cls)
         self._h = C.c_void_p()
         self.index_type = index_type
+        self.device = device
         buf = (C.c_char * len(data)).from_buffer_copy(data)
         _native.check(_native.lib().ds2i_gpu_index_open(C.cast(buf, C.c_void_p), len(data), index_type.encode(), device, C.byref(self._h)))
         return self
@@ -110,6 +112,17 @@ class Index:
                                                        None, None, C.byref(ms)))
         return int(offs[-1]), ms.value
 
+    def decode_lists_checksum(self, terms):
+        """Full decode left in HBM and reduced there: (postings, sum of docids, sum of freqs, kernel_ms)."""
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        sizes = self.list_sizes(terms)
+        offs = np.zeros(len(terms) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(sizes, dtype=np.uint64)
+        ms, sd, sf = C.c_float(), C.c_uint64(), C.c_uint64()
+        _native.check(_native.lib().ds2i_gpu_decode_lists_checksum(self._h, _p(terms, C.c_uint32), len(terms), _p(offs, C.c_uint64),
+                                                                C.byref(sd), C.byref(sf), C.byref(ms)))
+        return int(offs[-1]), int(sd.value), int(sf.value), ms.value
+
     def next_geq_batch(self, terms, bounds_per_list):
         """index[term] opened, then next_geq(b) for each b (non-decreasing).  Returns (docids, freqs, ms)."""
         terms = np.ascontiguousarray(terms, dtype=np.uint32)
@@ -157,19 +170,45 @@ class QueryBatch:
         self._h = C.c_void_p()
         self.nq = len(queries)
         self._keep = (index, wdata)
+        self._device = getattr(index, "device", 0)
         flat, offs = _flatten(queries)
         wh = wdata._h if wdata is not None else C.c_void_p()
         _native.check(_native.lib().ds2i_gpu_batch_prepare(index._h, wh, _p(flat, C.c_uint32), _p(offs, C.c_uint64), self.nq, C.byref(self._h)))
         self.h2d_bytes = flat.nbytes + offs.nbytes
 
-    def run(self, op, k=10, faithful=False):
+    def run(self, op, k=10, faithful=False, wait=True):
         """Evaluate `op` over the resident batch; returns the CUDA-event time in ms.  faithful=True
-        selects the literal one-candidate-at-a-time kernels (DS2I_RUN_FAITHFUL)."""
+        selects the literal one-candidate-at-a-time kernels (DS2I_RUN_FAITHFUL).  wait=False launches
+        without a host synchronisation (DS2I_RUN_ASYNC): the work is ordered on the device's default
+        stream, so a collective enqueued afterwards runs behind it; wait() returns the kernel time."""
         ms = C.c_float()
         self._k = k
         self._op = op
-        _native.check(_native.lib().ds2i_gpu_batch_run_ex(self._h, OPS.index(op), k, 1 if faithful else 0, C.byref(ms)))
+        flags = (1 if faithful else 0) | (0 if wait else 2)
+        _native.check(_native.lib().ds2i_gpu_batch_run_ex(self._h, OPS.index(op), k, flags, C.byref(ms)))
         return ms.value
+
+    def wait(self):
+        ms = C.c_float()
+        _native.check(_native.lib().ds2i_gpu_batch_wait(self._h, C.byref(ms)))
+        return ms.value
+
+    def device_fused(self, pad_to=None):
+        """The results of the last run as ONE torch uint8 CUDA tensor aliasing the library's buffer:
+        [counts nq x u64][scores nq*k x f32][docids nq*k x u32] (unranked operators: counts only).  pad_to: expose
+        that many bytes (the buffer is allocated for the largest k, so a shard can pad to the size of its peers)."""
+        import torch
+        p, n = C.c_void_p(), C.c_size_t()
+        _native.check(_native.lib().ds2i_gpu_batch_device_fused(self._h, C.byref(p), C.byref(n)))
+        nbytes = int(n.value) if pad_to is None else int(pad_to)
+        if nbytes > max(self.nq, 1) * (8 + 8 * 32):
+            raise ValueError("pad_to beyond the fused buffer")
+
+        class _Cai:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Cai(p.value, (nbytes,)), device=torch.device("cuda", self._device))
 
     def fetch(self):
         counts = np.zeros(max(self.nq, 1), dtype=np.uint64)
@@ -194,7 +233,7 @@ class QueryBatch:
             def __init__(self, ptr, shape, typestr):
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
 
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device("cuda", self._device)          # the index's device, whatever torch's current device is
         counts = torch.as_tensor(_Cai(pc.value, (self.nq,), "<i8"), device=dev)
         scores = torch.as_tensor(_Cai(ps.value, (self.nq, k), "<f4"), device=dev)
         if with_docids:
@@ -212,6 +251,46 @@ class QueryBatch:
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             _native.lib().ds2i_gpu_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """The index (and wand data) replicated over `ngpus` devices of this process; a batch is cut into cost-balanced shards,
+    evaluated concurrently and gathered over NCCL on the first device (ds2i_gpu_group_*)."""
+
+    def __init__(self, index_path, index_type, wand_path=None, ngpus=1, devices=None):
+        self._h = C.c_void_p()
+        dev = None
+        if devices is not None:
+            ngpus = len(devices)
+            dev = (C.c_int * ngpus)(*devices)
+        _native.check(_native.lib().ds2i_gpu_group_open(str(index_path).encode(), index_type.encode(),
+                                                     str(wand_path).encode() if wand_path else None, dev, ngpus, C.byref(self._h)))
+
+    def size(self):
+        return int(_native.lib().ds2i_gpu_group_size(self._h))
+
+    def query_batch(self, op, queries, k=10):
+        """Returns (counts, scores, docids, max per-GPU kernel ms) in the caller's query order."""
+        flat, offs = queries if isinstance(queries, tuple) else _flatten(queries)
+        nq = len(offs) - 1
+        counts = np.zeros(max(nq, 1), dtype=np.uint64)
+        scores = np.zeros((max(nq, 1), k), dtype=np.float32)
+        docids = np.full((max(nq, 1), k), 0xFFFFFFFF, dtype=np.uint32)
+        ms = C.c_float()
+        _native.check(_native.lib().ds2i_gpu_group_query_batch(self._h, OPS.index(op), k, _p(flat, C.c_uint32), _p(offs, C.c_uint64), nq,
+                                                            _p(counts, C.c_uint64), _p(scores, C.c_float), _p(docids, C.c_uint32), C.byref(ms)))
+        return counts[:nq], scores[:nq], docids[:nq], ms.value
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _native.lib().ds2i_gpu_group_close(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -67,6 +67,15 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def builder_writes(index_type):
+    """Whether ds2i_build can write `index_type` (ds2i_build types)."""
+    try:
+        r = subprocess.run([BUILDER, "types"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10)
+        return r.returncode == 0 and index_type in r.stdout.split()
+    except Exception:
+        return False
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

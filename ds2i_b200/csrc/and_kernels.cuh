@@ -20,6 +20,23 @@
 
 namespace ds2i_gpu {
 
+// algorithmic-work counters can be compiled out (-DDS2I_NO_STATS) to measure what they cost
+#ifdef DS2I_NO_STATS
+#define DS2I_STAT(x)
+#else
+#define DS2I_STAT(x) x
+#endif
+
+#ifdef DS2I_NIN_HIST
+// experiment: distribution of the probe regimes.  [0..7] probe steps by candidates answered (1, 2-3, 4-7, .., 64-128), [8] driver blocks,
+// [9..13] (driver block, list) visits by pending candidates at entry (1-8, 9-32, 33-64, 65-128), [16..23] visits by steps taken (1,2-3,4-7,...)
+__device__ unsigned long long g_hist[32];
+__device__ __forceinline__ uint32_t hist_bucket(uint32_t n) { return n ? 31u - __clz(n) : 0u; }
+#define DS2I_HIST(i, v) do { if (lane_id() == 0) atomicAdd(&g_hist[i], (unsigned long long)(v)); } while (0)
+#else
+#define DS2I_HIST(i, v)
+#endif
+
 constexpr uint32_t AND_CHUNK_BLOCKS = 32;     // blocks of the shortest list per work item
 
 // Work items are implicit: query sched[p] owns ceil(blocks of its shortest list / chunk_blocks) consecutive items; a warp
@@ -160,7 +177,7 @@ __device__ __forceinline__ void and_decode_docs(AndCtx& c, List* s, uint32_t slo
     if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, e1, e0 + consumed);
     __syncwarp();
     c.win_slot = slot; c.win_delta = off - e0;
-    c.c_docs_blocks += 1; c.c_bytes_docs += consumed;
+    DS2I_STAT(c.c_docs_blocks += 1; c.c_bytes_docs += consumed;)
 }
 
 // freqs - 1 of the current block of `s` -> the 128-word buffer at out_off.  Right after the docs decode the
@@ -178,7 +195,7 @@ __device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const List* s, uint3
     }
     bool prefix;
     const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, freqs_off + c.win_delta, size, 0xffffffffu, out_off, c.stack_off, prefix);
-    c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed;
+    DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed;)
     return prefix;
 }
 
@@ -194,7 +211,7 @@ __device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint
     uint32_t bi = lo + lane;
     uint2 en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
     unsigned hit = __ballot_sync(FULL, en.x >= bound);
-    c_maxs += 32;
+    DS2I_STAT(c_maxs += 32;)
     if (!hit) {
         uint32_t l2 = lo + 32, hi = nblocks - 1;     // invariant: max[hi] >= bound, every block < l2 has max < bound
         while (hi - l2 >= 31) {
@@ -202,7 +219,7 @@ __device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint
             const uint32_t probe = l2 + uint32_t((uint64_t(span) * (lane + 1)) / 33);
             const uint32_t m = __ldg(bd + probe).x;
             const unsigned h = __ballot_sync(FULL, m >= bound);
-            c_maxs += 32;
+            DS2I_STAT(c_maxs += 32;)
             if (h) {
                 const uint32_t f = __ffs(h) - 1;
                 const uint32_t nh = __shfl_sync(FULL, probe, f);
@@ -217,7 +234,7 @@ __device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint
         bi = lo + lane;
         en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
         hit = __ballot_sync(FULL, en.x >= bound) & ~1u;
-        c_maxs += 32;
+        DS2I_STAT(c_maxs += 32;)
     }
     const uint32_t f = __ffs(hit) - 1;
     BlockMeta r;
@@ -349,6 +366,10 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                 const uint32_t last_max = s->last_max;
                 const float qwi = RANKED ? ws->qw[i] : 0.f;
                 uint32_t pending = alive;  // alive candidates not yet looked up in list i
+#ifdef DS2I_NIN_HIST
+                uint32_t h_steps = 0;
+                { const uint32_t np = __reduce_add_sync(FULL, __popc(pending)); DS2I_HIST(9 + (np <= 8 ? 0 : np <= 32 ? 1 : np <= 64 ? 2 : 3), 1); }
+#endif
                 while (true) {
                     uint32_t mine = 0xffffffffu;
 #pragma unroll
@@ -376,6 +397,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                         if ((pending & (1u << j)) && cand[j] <= cur_max) inb |= 1u << j;
                     pending &= ~inb;
                     const uint32_t nin = __reduce_add_sync(FULL, __popc(inb));
+#ifdef DS2I_NIN_HIST
+                    DS2I_HIST(hist_bucket(nin), 1); ++h_steps;
+#endif
                     uint32_t hitmask = 0, pos[4] = {0, 0, 0, 0};
                     if (nin == 1) {
                         // the usual case when list i is much longer than the driving list: one candidate per block,
@@ -419,7 +443,11 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                         __syncwarp();
                     }
                 }
+#ifdef DS2I_NIN_HIST
+                DS2I_HIST(16 + hist_bucket(h_steps), 1); DS2I_HIST(24, h_steps);
+#endif
             }
+            DS2I_HIST(8, 1);
 
             const unsigned nalive = __popc(alive);
             const unsigned total = __reduce_add_sync(FULL, nalive);
@@ -427,9 +455,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             if (RANKED) {
                 if (!total) {
                     // the reference never decodes the freqs of a block without a match: not algorithmic work
-                    c.c_freqs_blocks -= 1; c.c_bytes_freqs -= f0_bytes;
+                    DS2I_STAT(c.c_freqs_blocks -= 1; c.c_bytes_freqs -= f0_bytes;)
                 } else {
-                    c.c_scored += total;
+                    DS2I_STAT(c.c_scored += total;)
                     if (nt == 1) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)

@@ -10,6 +10,11 @@ namespace ds2i_gpu {
 
 constexpr uint32_t STAGE_BYTES = 1280;                 // staged window (16-B aligned superset of a block pair)
 constexpr uint32_t STAGE_WORDS = STAGE_BYTES / 4 + 4;  // + slack for the w+1 word of unaligned reads
+// Largest [docs | freqs] pair of 128-value blocks per codec: OptPFD raw blocks 2 x 4*129 = 1032 B (newpfor.h:204-209),
+// varint-G8IU 2 x 64 groups x 9 B = 1152 B, QMX 2 x (512 B of 32-bit stripes + <= 32 keys + 2 length bytes) = 1092 B,
+// interpolative (<= 128 values of < 32 bits) below those; + up to 15 B of alignment slack at either end of the window.
+// ds2i_gpu_index_open refuses an index with a larger pair (DS2I_E_LIMIT), so the clamp in and_stage / stage_range never cuts data.
+static_assert(STAGE_BYTES >= 2 * 576 + 30, "the staging window must hold the largest block pair of every codec");
 
 struct ListDir {            // per posting list, built once at load time (host) from the EF endpoints
     uint64_t maxs_off;      // byte offset of block_maxs[] inside m_lists (just after TightVByte(n))

@@ -689,7 +689,8 @@ int main(int argc, char** argv) {
             }
             return 0;
         }
-        fprintf(stderr, "usage: ds2i_build gen|index|wand|synth|shard ... (see the header of builder.cpp)\n");
+        if (cmd == "types") { printf("block_optpfor block_interpolative\n"); return 0; }      // index types this builder writes
+        fprintf(stderr, "usage: ds2i_build gen|index|wand|synth|shard|types ... (see the header of builder.cpp)\n");
         return 1;
     } catch (std::exception const& e) {
         fprintf(stderr, "ds2i_build: %s\n", e.what());

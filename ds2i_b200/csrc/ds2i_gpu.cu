@@ -14,9 +14,12 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include <dlfcn.h>
 #include <fcntl.h>
+#include <nccl.h>          // types only: the library is dlopen'ed by the multi-GPU entry points, never linked
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -55,14 +58,34 @@ static void tune_mem_pool(int device) {
     }
 }
 
+// makes `device` current for the scope and restores the caller's device afterwards: handles may live on different GPUs
+// of one process (ds2i_gpu_query_batch_multi), and stream 0 / cudaFreeAsync act on the CURRENT device
+struct device_scope {
+    int prev = -1;
+    explicit device_scope(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device); else prev = -1;
+    }
+    ~device_scope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <typename T>
 struct dev_buf {
     T* p = nullptr;
     size_t n = 0;
-    ~dev_buf() { if (p) cudaFreeAsync(p, 0); }
+    int device = -1;          // the device the buffer was allocated on
+    void release() {
+        if (!p) return;
+        device_scope ds(device);
+        cudaFreeAsync(p, 0);
+        p = nullptr;
+    }
+    ~dev_buf() { release(); }
     cudaError_t alloc(size_t count) {
-        if (p) { cudaFreeAsync(p, 0); p = nullptr; }
+        release();
         n = count;
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return e;
         return cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T), 0);
     }
     cudaError_t upload(std::vector<T> const& v) {
@@ -70,6 +93,16 @@ struct dev_buf {
         if (e != cudaSuccess || v.empty()) return e;
         return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, 0);
     }
+};
+
+struct cuda_event {            // RAII: error paths must not leak events
+    cudaEvent_t e = nullptr;
+    ~cuda_event() { if (e) cudaEventDestroy(e); }
+    cudaError_t create() { return cudaEventCreate(&e); }
+};
+struct cuda_free_guard {       // RAII for a plain cudaMalloc'ed pointer
+    void* p = nullptr;
+    ~cuda_free_guard() { if (p) cudaFree(p); }
 };
 
 struct mapped_file {
@@ -84,6 +117,22 @@ struct mapped_file {
         if (n && m == MAP_FAILED) { p = nullptr; return false; }
         p = static_cast<const uint8_t*>(m);
         return true;
+    }
+};
+
+// pinned host staging memory, grown on demand and kept for the life of the index handle (one batch call in flight per
+// handle): every per-batch upload is ONE cudaMemcpyAsync from here instead of a dozen pageable copies
+struct pinned_arena {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    ~pinned_arena() { if (p) cudaFreeHost(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want);
+        if (e == cudaSuccess) cap = want;
+        return e;
     }
 };
 
@@ -108,6 +157,8 @@ struct ds2i_gpu_index {
     // opt (partitioned Elias-Fano) index
     std::unique_ptr<PefIndexHost> pef;
     int sm_count = 148;
+    pinned_arena staging;     // host staging of the per-batch uploads / downloads
+    std::mutex staging_mu;
 };
 
 struct ds2i_gpu_wand {
@@ -118,6 +169,8 @@ struct ds2i_gpu_wand {
     DevWand dev{};
 };
 
+template <typename T> struct dev_view { T* p = nullptr; };     // a typed window of the batch's device arena
+
 struct ds2i_gpu_batch {
     ds2i_gpu_index* index = nullptr;
     ds2i_gpu_wand* wand = nullptr;
@@ -125,26 +178,40 @@ struct ds2i_gpu_batch {
     int max_terms = 1;
     uint32_t last_k = 0;
     bool last_ranked = false;
-    dev_buf<uint32_t> q_begin, term, sched, work_counter;
-    dev_buf<float> q_weight, max_weight, out_scores;
-    dev_buf<uint8_t> ord_size, ord_maxw;
-    dev_buf<uint64_t> out_counts;
-    dev_buf<uint32_t> out_docids;
-    dev_buf<unsigned long long> stats;
+    bool pending = false;          // an asynchronous run has been launched and not waited for yet
+    // ONE device allocation per batch: the uploaded descriptors first (one H2D copy), then the device-only buffers
+    dev_buf<uint8_t> arena;
+    dev_view<uint32_t> q_begin, term, sched, work_counter;
+    dev_view<float> q_weight, max_weight;
+    dev_view<uint8_t> ord_size, ord_maxw;
+    // results of the last run, fused so that one collective / one D2H copy moves them: [counts: nq u64][scores: nq*k f32][docids: nq*k u32]
+    dev_view<uint8_t> out_fused;
+    dev_view<uint64_t> out_counts;
+    dev_view<float> out_scores;
+    dev_view<uint32_t> out_docids;
+    dev_view<unsigned long long> stats;
     // block-at-a-time conjunctive path: work items = (query, chunk of blocks of its shortest list)
-    dev_buf<uint32_t> and_gstart, and_item_begin, and_item_counts, and_item_sizes;
+    dev_view<uint32_t> and_gstart, and_item_begin, and_item_counts, and_item_sizes;
     dev_buf<float> and_item_scores;
     size_t and_item_scores_k = 0;
     uint32_t n_and_items = 0, and_chunk = AND_CHUNK_BLOCKS;
     // block-parallel union path (wand / maxscore): work items = (query, driving list, run of its blocks), implicit
-    dev_buf<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_item_begin, un_item_sizes, un_threshold;
-    dev_buf<float> un_item_scores, un_ub;
+    dev_view<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_item_begin, un_item_sizes, un_threshold;
+    dev_view<float> un_ub;
+    dev_buf<float> un_item_scores;
     size_t un_item_scores_k = 0;      // k the partial top-k buffer was sized for
     uint32_t n_un_items = 0, n_un_groups = 0, un_item_blocks = 64;
     unsigned items_built = 3;      // which work-item lists exist (bit 0 conjunctive, bit 1 union)
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~ds2i_gpu_batch() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
+    // the fused result buffer is laid out for the k of the run
+    void layout_outputs(uint32_t k) {
+        out_counts.p = reinterpret_cast<uint64_t*>(out_fused.p);
+        out_scores.p = reinterpret_cast<float*>(out_fused.p + size_t(nq) * 8);
+        out_docids.p = reinterpret_cast<uint32_t*>(out_fused.p + size_t(nq) * 8 + size_t(nq) * k * 4);
+    }
+    size_t fused_bytes(uint32_t k) const { return size_t(nq) * (8 + 8 * size_t(k)); }
 };
 
 static int codec_from_type(const char* t, int* kind) {
@@ -170,6 +237,11 @@ extern "C" int ds2i_gpu_op_from_name(const char* name) {
     if (!name) return DS2I_E_ARG;
     for (int i = 0; i < 8; ++i) if (!strcmp(name, names[i])) return i;
     return DS2I_E_ARG;
+}
+
+extern "C" int ds2i_gpu_index_type_known(const char* index_type) {
+    int kind;
+    return index_type && codec_from_type(index_type, &kind) >= 0 ? 1 : 0;
 }
 
 extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const char* index_type, int device,
@@ -212,15 +284,24 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
             uint64_t maxs_off = uint64_t(q - f.lists);
             uint64_t data_off = maxs_off + 4 * blocks + 4 * (blocks - 1);
             if (data_off > end) throw format_error("posting list header exceeds the list");
+            if (end - data_off > 0xffffffffull) return fail(DS2I_E_LIMIT, "posting list " + std::to_string(i) + " holds 4 GB or more of block data");
             ix->host_dir[i] = ListDir{maxs_off, n, uint32_t(end - data_off)};
             if (bdir.size() + blocks > 0xfffffff0ull) return fail(DS2I_E_LIMIT, "more than 2^32 blocks in the index");
             bfirst[i] = uint32_t(bdir.size());
             const uint8_t* maxs = f.lists + maxs_off;
             const uint8_t* ends = maxs + 4 * blocks;
+            uint32_t e_prev = 0;
             for (uint64_t b = 0; b < blocks; ++b) {
                 uint32_t m, e = uint32_t(end - data_off);
                 memcpy(&m, maxs + 4 * b, 4);
                 if (b + 1 < blocks) memcpy(&e, ends + 4 * b, 4);
+                // the kernels stage every [docs | freqs] block pair as one 16-B aligned window of at most STAGE_BYTES
+                // (and_stage, stage_range): endpoints that run backwards, past the list, or a pair that cannot fit the
+                // window would be decoded from stale shared memory, so they are refused here
+                if (e < e_prev || e > uint32_t(end - data_off)) throw format_error("block endpoints of list " + std::to_string(i) + " are not monotone");
+                if (uint64_t(e - e_prev) + 30 > STAGE_BYTES)
+                    return fail(DS2I_E_LIMIT, "block pair of " + std::to_string(e - e_prev) + " bytes in list " + std::to_string(i) + " exceeds the staging window");
+                e_prev = e;
                 bdir.push_back(make_uint2(m, e));
             }
         }
@@ -249,7 +330,7 @@ extern "C" int ds2i_gpu_index_open_file(const char* path, const char* index_type
     return ds2i_gpu_index_open(m.p, m.n, index_type, device, out);
 }
 
-extern "C" void ds2i_gpu_index_close(ds2i_gpu_index* ix) { delete ix; }
+extern "C" void ds2i_gpu_index_close(ds2i_gpu_index* ix) { if (ix) { device_scope ds(ix->device); delete ix; } }
 extern "C" uint64_t ds2i_gpu_index_size(const ds2i_gpu_index* ix) { return ix ? ix->size : 0; }
 extern "C" uint64_t ds2i_gpu_index_num_docs(const ds2i_gpu_index* ix) { return ix ? ix->num_docs : 0; }
 extern "C" uint64_t ds2i_gpu_index_device_bytes(const ds2i_gpu_index* ix) { return ix ? ix->device_bytes : 0; }
@@ -306,7 +387,7 @@ extern "C" int ds2i_gpu_wand_open_file(const char* path, int device, ds2i_gpu_wa
     if (!m.open(path)) return fail(DS2I_E_ARG, std::string("cannot open ") + path);
     return ds2i_gpu_wand_open(m.p, m.n, device, out);
 }
-extern "C" void ds2i_gpu_wand_close(ds2i_gpu_wand* w) { delete w; }
+extern "C" void ds2i_gpu_wand_close(ds2i_gpu_wand* w) { if (w) { device_scope ds(w->device); delete w; } }
 
 // ------------------------------------------------------------------------------------------------
 // bm25::query_term_weight (bm25.hpp:17-24), evaluated on the host with the same libm as the reference
@@ -325,20 +406,26 @@ static double now_ms() {
 static bool trace_on() { static const bool t = getenv("DS2I_GPU_TRACE") != nullptr; return t; }
 
 // cudaFuncSetAttribute + the occupancy query are not free: do them once per (kernel, shared-memory size)
+// (and per DEVICE: the opt-in shared-memory limit and the occupancy are per-device state of the current context)
 static int cached_blocks_per_sm(const void* kern, int threads, size_t smem, int* out) {
-    struct key { const void* k; size_t s; int v; };
+    struct key { const void* k; size_t s; int dev; int v; };
     static std::vector<key> cache;
     static std::mutex mu;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
-    for (auto const& c : cache) if (c.k == kern && c.s == smem) { *out = c.v; return DS2I_OK; }
+    for (auto const& c : cache) if (c.k == kern && c.s == smem && c.dev == dev) { *out = c.v; return DS2I_OK; }
     // the opt-in limit is per-function state and the last call wins: only ever raise it, or a batch with few terms
     // would lower it under a later batch that needs the larger window again
     size_t raised = 0;
-    for (auto const& c : cache) if (c.k == kern) raised = std::max(raised, c.s);
+    for (auto const& c : cache) if (c.k == kern && c.dev == dev) raised = std::max(raised, c.s);
     if (smem > raised) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+#ifdef DS2I_CARVEOUT_MAX
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#endif
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    cache.push_back(key{kern, smem, per_sm});
+    cache.push_back(key{kern, smem, dev, per_sm});
     *out = per_sm;
     return DS2I_OK;
 }
@@ -352,6 +439,79 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     return batch_prepare_impl(ix, wand, terms, query_offsets, nq, 3u, out);
 }
 
+// number of host threads for the per-query preparation (DS2I_GPU_HOST_THREADS overrides; small batches stay single-threaded)
+static unsigned prepare_threads(size_t nq) {
+    static const unsigned hw = [] {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char* ev = getenv("DS2I_GPU_HOST_THREADS")) n = unsigned(std::max(1, atoi(ev)));
+        return std::max(1u, std::min(n, 16u));
+    }();
+    return unsigned(std::max<size_t>(1, std::min<size_t>(hw, nq / 512)));
+}
+
+// what one host thread produces for its contiguous range of queries
+struct prep_part {
+    std::vector<uint32_t> term, nt;          // distinct terms (query_freqs order); distinct terms per query
+    std::vector<float> q_weight, max_weight;
+    std::vector<uint8_t> ord_size, ord_maxw;
+    std::vector<uint64_t> cost, shortest;
+    int max_terms = 1;
+    int rc = DS2I_OK;
+    std::string err;
+};
+
+static void prepare_range(const ds2i_gpu_index* ix, const ds2i_gpu_wand* wand, const uint32_t* terms, const uint64_t* query_offsets,
+                          size_t q0, size_t q1, prep_part& out) {
+    struct ent { uint64_t n; float mw; uint8_t pos; uint64_t local_n; };   // n: the list size the reference would see (collection-wide df for a shard)
+    std::vector<uint32_t> tmp;
+    ent ents[MAX_TERMS], by_size[MAX_TERMS], by_mw[MAX_TERMS];
+    out.nt.reserve(q1 - q0); out.cost.reserve(q1 - q0); out.shortest.reserve(q1 - q0);
+    for (size_t q = q0; q < q1; ++q) {
+        if (query_offsets[q + 1] < query_offsets[q]) { out.rc = DS2I_E_ARG; out.err = "query_offsets not monotone"; return; }
+        tmp.assign(terms + query_offsets[q], terms + query_offsets[q + 1]);
+        std::sort(tmp.begin(), tmp.end());               // query_freqs (queries.hpp:136-150)
+        uint32_t ne = 0;
+        uint64_t cost = 0;
+        for (size_t i = 0; i < tmp.size();) {
+            size_t j = i;
+            while (j < tmp.size() && tmp[j] == tmp[i]) ++j;
+            uint32_t t = tmp[i];
+            if (t >= ix->size) { out.rc = DS2I_E_ARG; out.err = "term id out of range in query " + std::to_string(q); return; }
+            if (wand && t >= wand->num_terms) { out.rc = DS2I_E_ARG; out.err = "term id beyond wand data"; return; }
+            const uint64_t local_n = list_size_of(ix, t);
+            // a document-partitioned shard scores with the statistics of the whole collection (ds2i_gpu_index_set_global_stats)
+            const uint64_t n = ix->g_df.empty() ? local_n : ix->g_df[t];
+            float qw = query_term_weight(j - i, n, ix->g_num_docs ? ix->g_num_docs : ix->num_docs);
+            float mw = wand ? qw * wand->h_max_term_weight[t] : 0.f;
+            if (ne >= uint32_t(MAX_TERMS)) {
+                out.rc = DS2I_E_LIMIT;
+                out.err = "query " + std::to_string(q) + " has more than " + std::to_string(MAX_TERMS) + " distinct terms";
+                return;
+            }
+            ents[ne] = ent{n, mw, uint8_t(ne), local_n};
+            ++ne;
+            out.term.push_back(t); out.q_weight.push_back(qw); out.max_weight.push_back(mw);
+            cost += local_n;
+            i = j;
+        }
+        out.max_terms = std::max<int>(out.max_terms, int(ne));
+        out.nt.push_back(ne);
+        // the reference's own std::sort calls, on the same keys in the same initial order (queries.hpp:357-360, 521-524)
+        std::copy(ents, ents + ne, by_size); std::copy(ents, ents + ne, by_mw);
+        std::sort(by_size, by_size + ne, [](ent const& l, ent const& r) { return l.n < r.n; });
+        std::sort(by_mw, by_mw + ne, [](ent const& l, ent const& r) { return l.mw < r.mw; });
+        for (uint32_t i = 0; i < ne; ++i) { out.ord_size.push_back(by_size[i].pos); out.ord_maxw.push_back(by_mw[i].pos); }
+        out.cost.push_back(cost);
+        out.shortest.push_back(ne ? by_size[0].local_n : 0);
+    }
+}
+
+// bump allocator over the staging / device arena: every array starts 256-B aligned
+struct arena_layout {
+    size_t bytes = 0;
+    size_t take(size_t n) { size_t o = bytes; bytes = (bytes + n + 255) & ~size_t(255); return o; }
+};
+
 static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uint32_t* terms,
                               const uint64_t* query_offsets, size_t nq, unsigned which, ds2i_gpu_batch** out) {
     if (!ix || !out || !query_offsets || (!terms && nq && query_offsets[nq])) return fail(DS2I_E_ARG, "null argument");
@@ -362,60 +522,83 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     b->index = ix; b->wand = wand; b->nq = uint32_t(nq); b->items_built = which;
     const double tp0 = now_ms();
 
-    std::vector<uint32_t> q_begin(nq + 1, 0), term, sched(nq);
-    std::vector<float> q_weight, max_weight;
-    std::vector<uint8_t> ord_size, ord_maxw;
-    std::vector<uint64_t> cost(nq, 0), shortest(nq, 0);
-    struct ent { uint64_t n; float mw; uint8_t pos; uint64_t local_n; };   // n: the list size the reference would see (collection-wide df for a shard)
-    std::vector<uint32_t> tmp;
-    std::vector<ent> ents;
-    int max_terms = 1;
-    for (size_t q = 0; q < nq; ++q) {
-        if (query_offsets[q + 1] < query_offsets[q]) return fail(DS2I_E_ARG, "query_offsets not monotone");
-        tmp.assign(terms + query_offsets[q], terms + query_offsets[q + 1]);
-        std::sort(tmp.begin(), tmp.end());               // query_freqs (queries.hpp:136-150)
-        ents.clear();
-        for (size_t i = 0; i < tmp.size();) {
-            size_t j = i;
-            while (j < tmp.size() && tmp[j] == tmp[i]) ++j;
-            uint32_t t = tmp[i];
-            if (t >= ix->size) return fail(DS2I_E_ARG, "term id out of range in query " + std::to_string(q));
-            if (wand && t >= wand->num_terms) return fail(DS2I_E_ARG, "term id beyond wand data");
-            const uint64_t local_n = list_size_of(ix, t);
-            // a document-partitioned shard scores with the statistics of the whole collection (ds2i_gpu_index_set_global_stats)
-            const uint64_t n = ix->g_df.empty() ? local_n : ix->g_df[t];
-            float qw = query_term_weight(j - i, n, ix->g_num_docs ? ix->g_num_docs : ix->num_docs);
-            float mw = wand ? qw * wand->h_max_term_weight[t] : 0.f;
-            if (ents.size() >= size_t(MAX_TERMS))
-                return fail(DS2I_E_LIMIT, "query " + std::to_string(q) + " has more than " + std::to_string(MAX_TERMS) + " distinct terms");
-            ents.push_back(ent{n, mw, uint8_t(ents.size()), local_n});
-            term.push_back(t); q_weight.push_back(qw); max_weight.push_back(mw);
-            cost[q] += local_n;
-            i = j;
-        }
-        max_terms = std::max<int>(max_terms, int(ents.size()));
-        q_begin[q + 1] = uint32_t(term.size());
-        // the reference's own std::sort calls, on the same keys in the same initial order
-        std::vector<ent> by_size(ents), by_mw(ents);
-        std::sort(by_size.begin(), by_size.end(), [](ent const& l, ent const& r) { return l.n < r.n; });
-        std::sort(by_mw.begin(), by_mw.end(), [](ent const& l, ent const& r) { return l.mw < r.mw; });
-        for (auto const& e : by_size) ord_size.push_back(e.pos);
-        for (auto const& e : by_mw) ord_maxw.push_back(e.pos);
-        shortest[q] = ents.empty() ? 0 : by_size[0].local_n;
+    // ---- per-query host work, on several threads (contiguous ranges, so the parts concatenate in query order)
+    const unsigned nthreads = prepare_threads(nq);
+    std::vector<prep_part> parts(nthreads);
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; ++t)
+            pool.emplace_back(prepare_range, ix, wand, terms, query_offsets, nq * t / nthreads, nq * (t + 1) / nthreads, std::ref(parts[t]));
+        prepare_range(ix, wand, terms, query_offsets, 0, nq / nthreads, parts[0]);
+        for (auto& th : pool) th.join();
     }
-    std::iota(sched.begin(), sched.end(), 0u);
-    std::stable_sort(sched.begin(), sched.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+    size_t nterms_total = 0;
+    int max_terms = 1;
+    for (auto const& pt : parts) {
+        if (pt.rc != DS2I_OK) return fail(pt.rc, pt.err);
+        nterms_total += pt.term.size();
+        max_terms = std::max(max_terms, pt.max_terms);
+    }
+    if (nterms_total > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many query terms in one batch");
+    b->max_terms = max_terms;
+    const size_t T = nterms_total;
+    const size_t G = (which & 2u) ? T : 0;            // union path: one group per query term
+
+    // ---- layout of the uploaded part, then of the device-only part
+    arena_layout lay;
+    const size_t o_q_begin = lay.take((nq + 1) * 4), o_term = lay.take(T * 4), o_sched = lay.take(nq * 4), o_qw = lay.take(T * 4),
+                 o_mw = lay.take(T * 4), o_os = lay.take(T), o_om = lay.take(T), o_and_gstart = lay.take((nq + 1) * 4),
+                 o_and_begin = lay.take((nq + 1) * 4), o_un_gstart = lay.take((G + 1) * 4), o_un_gterm = lay.take(G * 4),
+                 o_un_gquery = lay.take(G * 4), o_un_gbase = lay.take(G * 4), o_un_begin = lay.take((nq + 1) * 4), o_un_ub = lay.take(T * 4);
+    const size_t upload_bytes = lay.bytes;
+
+    std::lock_guard<std::mutex> staging_lock(ix->staging_mu);
+    CUDA_TRY(ix->staging.reserve(upload_bytes));
+    uint8_t* h = ix->staging.p;
+    uint32_t* q_begin = reinterpret_cast<uint32_t*>(h + o_q_begin);
+    uint32_t* term = reinterpret_cast<uint32_t*>(h + o_term);
+    uint32_t* sched = reinterpret_cast<uint32_t*>(h + o_sched);
+    float* q_weight = reinterpret_cast<float*>(h + o_qw);
+    float* max_weight = reinterpret_cast<float*>(h + o_mw);
+    uint8_t* ord_size = h + o_os;
+    uint8_t* ord_maxw = h + o_om;
+    std::vector<uint64_t> cost(nq), shortest(nq);
+    {
+        size_t q = 0, t = 0;
+        q_begin[0] = 0;
+        for (auto const& pt : parts) {
+            if (!pt.term.empty()) {
+                memcpy(term + t, pt.term.data(), pt.term.size() * 4);
+                memcpy(q_weight + t, pt.q_weight.data(), pt.term.size() * 4);
+                memcpy(max_weight + t, pt.max_weight.data(), pt.term.size() * 4);
+                memcpy(ord_size + t, pt.ord_size.data(), pt.term.size());
+                memcpy(ord_maxw + t, pt.ord_maxw.data(), pt.term.size());
+            }
+            for (size_t i = 0; i < pt.nt.size(); ++i, ++q) {
+                t += pt.nt[i];
+                q_begin[q + 1] = uint32_t(t);
+                cost[q] = pt.cost[i]; shortest[q] = pt.shortest[i];
+            }
+        }
+    }
+    // processing order: costliest queries first (ties keep the query order)
+    {
+        std::iota(sched, sched + nq, 0u);
+        std::stable_sort(sched, sched + nq, [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+    }
 
     const double tp1 = now_ms();
     // work items of the conjunctive path (DS2I_GPU_AND_CHUNK_BLOCKS: blocks of the shortest list per item, <= 32)
     uint32_t and_chunk = AND_CHUNK_BLOCKS;
     if (const char* ev = getenv("DS2I_GPU_AND_CHUNK_BLOCKS")) and_chunk = std::min<uint32_t>(32, std::max<uint32_t>(1, uint32_t(atoi(ev))));
     b->and_chunk = and_chunk;
-    std::vector<uint32_t> item_begin(nq + 1, 0), and_gstart(nq + 1, 0);
+    uint32_t* item_begin = reinterpret_cast<uint32_t*>(h + o_and_begin);
+    uint32_t* and_gstart = reinterpret_cast<uint32_t*>(h + o_and_gstart);
     {
         uint64_t nitems = 0;
-        for (size_t q = 0; q < nq && (which & 1u); ++q) {
-            nitems += ((shortest[q] + BLOCK - 1) / BLOCK + and_chunk - 1) / and_chunk;
+        item_begin[0] = 0; and_gstart[0] = 0;
+        for (size_t q = 0; q < nq; ++q) {
+            if (which & 1u) nitems += ((shortest[q] + BLOCK - 1) / BLOCK + and_chunk - 1) / and_chunk;
             if (nitems > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many work items in one batch");
             item_begin[q + 1] = uint32_t(nitems);
         }
@@ -423,15 +606,17 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         for (size_t p = 0; p < nq; ++p) and_gstart[p + 1] = and_gstart[p] + (item_begin[sched[p] + 1] - item_begin[sched[p]]);
         b->n_and_items = uint32_t(nitems);
     }
-    CUDA_TRY(b->and_gstart.upload(and_gstart)); CUDA_TRY(b->and_item_begin.upload(item_begin));
-    CUDA_TRY(b->and_item_counts.alloc(b->n_and_items)); CUDA_TRY(b->and_item_sizes.alloc(b->n_and_items));
 
     // work items of the union path: (query, driving list, run of its blocks), highest-weight lists first.  Only the
     // groups (one per query term) are materialised; the kernel derives the items from the prefix array.
     {
-        const size_t nterms_total = term.size();
-        std::vector<float> ub(nterms_total, 0.f);
-        std::vector<uint32_t> ubegin(nq + 1, 0), gbase(nterms_total, 0), gchunks(nterms_total, 0);
+        float* ub = reinterpret_cast<float*>(h + o_un_ub);
+        uint32_t* ubegin = reinterpret_cast<uint32_t*>(h + o_un_begin);
+        uint32_t* gstart = reinterpret_cast<uint32_t*>(h + o_un_gstart);
+        uint32_t* gterm = reinterpret_cast<uint32_t*>(h + o_un_gterm);
+        uint32_t* gquery = reinterpret_cast<uint32_t*>(h + o_un_gquery);
+        uint32_t* gres = reinterpret_cast<uint32_t*>(h + o_un_gbase);
+        std::vector<uint32_t> gbase(T, 0), gchunks(T, 0);
         // postings per work item; DS2I_GPU_UNION_ITEM_POSTINGS overrides it (tests use a tiny value to
         // exercise the splitting path on small collections)
         uint64_t per_item = 8192;
@@ -440,13 +625,15 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         b->un_item_blocks = item_blocks;
         std::vector<uint32_t> level_count(MAX_TERMS + 1, 0);
         uint64_t nitems = 0;
-        for (size_t q = 0; q < nq && (which & 2u); ++q) {
+        ubegin[0] = 0;
+        for (size_t q = 0; q < nq; ++q) {
             const uint32_t t0 = q_begin[q], nt = q_begin[q + 1] - t0;
             float acc = 0.f;
             for (uint32_t i = 0; i < nt; ++i) {          // queries.hpp:526-530, same sequential fp32 sum; slot i = i-th list by max_weight
                 const float mw = max_weight[t0 + ord_maxw[t0 + i]];
                 acc = i ? acc + mw : mw;
                 ub[t0 + i] = acc;
+                if (!(which & 2u)) continue;
                 const uint64_t nb = (list_size_of(ix, term[t0 + ord_maxw[t0 + i]]) + BLOCK - 1) / BLOCK;
                 gchunks[t0 + i] = uint32_t((nb + item_blocks - 1) / item_blocks);
                 gbase[t0 + i] = uint32_t(nitems);
@@ -457,41 +644,49 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
             ubegin[q + 1] = uint32_t(nitems);
         }
         // processing order: level by level (level 0 = each query's highest-weight list), costliest queries first inside a level
-        const size_t ngroups = (which & 2u) ? nterms_total : 0;
-        std::vector<uint32_t> gterm(ngroups), gquery(ngroups), gres(ngroups), gstart(ngroups + 1, 0);
-        {
+        gstart[0] = 0;
+        if (G) {
             std::vector<uint32_t> level_pos(MAX_TERMS + 1, 0);
             for (int l = 1; l <= MAX_TERMS; ++l) level_pos[l] = level_pos[l - 1] + level_count[l - 1];
-            for (uint32_t qi : sched) {
-                if (!ngroups) break;
+            for (size_t p = 0; p < nq; ++p) {
+                const uint32_t qi = sched[p];
                 const uint32_t t0 = q_begin[qi], nt = q_begin[qi + 1] - t0;
                 for (uint32_t i = 0; i < nt; ++i) {
                     const uint32_t pos = level_pos[nt - 1 - i]++;
                     gterm[pos] = t0 + i; gquery[pos] = qi; gres[pos] = gbase[t0 + i]; gstart[pos + 1] = gchunks[t0 + i];
                 }
             }
-            for (size_t g = 0; g < ngroups; ++g) gstart[g + 1] += gstart[g];
+            for (size_t g = 0; g < G; ++g) gstart[g + 1] += gstart[g];
         }
-        b->n_un_items = uint32_t(nitems); b->n_un_groups = uint32_t(ngroups);
-        CUDA_TRY(b->un_gstart.upload(gstart)); CUDA_TRY(b->un_gterm.upload(gterm)); CUDA_TRY(b->un_gquery.upload(gquery));
-        CUDA_TRY(b->un_gbase.upload(gres)); CUDA_TRY(b->un_item_begin.upload(ubegin));
-        CUDA_TRY(b->un_ub.upload(ub));
-        CUDA_TRY(b->un_item_sizes.alloc(nitems));
-        CUDA_TRY(b->un_threshold.alloc(nq));
+        b->n_un_items = uint32_t(nitems); b->n_un_groups = uint32_t(G);
     }
-
     const double tp2 = now_ms();
-    b->max_terms = max_terms;
-    CUDA_TRY(b->q_begin.upload(q_begin)); CUDA_TRY(b->term.upload(term)); CUDA_TRY(b->sched.upload(sched));
-    CUDA_TRY(b->q_weight.upload(q_weight)); CUDA_TRY(b->max_weight.upload(max_weight));
-    CUDA_TRY(b->ord_size.upload(ord_size)); CUDA_TRY(b->ord_maxw.upload(ord_maxw));
-    CUDA_TRY(b->work_counter.alloc(4));
-    CUDA_TRY(b->out_counts.alloc(nq)); CUDA_TRY(b->out_scores.alloc(nq * MAX_K)); CUDA_TRY(b->out_docids.alloc(nq * MAX_K));
-    CUDA_TRY(b->stats.alloc(8));
-    CUDA_TRY(cudaMemset(b->stats.p, 0, 8 * sizeof(unsigned long long)));
+
+    // ---- device arena: the uploaded prefix + the device-only buffers, one allocation, one H2D copy
+    const size_t o_counter = lay.take(16), o_stats = lay.take(16 * 8), o_and_counts = lay.take(size_t(b->n_and_items) * 4),
+                 o_and_sizes = lay.take(size_t(b->n_and_items) * 4), o_un_sizes = lay.take(size_t(b->n_un_items) * 4),
+                 o_un_thr = lay.take(std::max<size_t>(nq, 1) * 4), o_fused = lay.take(nq * (8 + 8 * size_t(MAX_K)));
+    CUDA_TRY(b->arena.alloc(lay.bytes));
+    uint8_t* d = b->arena.p;
+    if (upload_bytes) CUDA_TRY(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemsetAsync(d + o_counter, 0, o_and_counts - o_counter, 0));          // work counters + stats
+    b->q_begin.p = reinterpret_cast<uint32_t*>(d + o_q_begin); b->term.p = reinterpret_cast<uint32_t*>(d + o_term);
+    b->sched.p = reinterpret_cast<uint32_t*>(d + o_sched); b->q_weight.p = reinterpret_cast<float*>(d + o_qw);
+    b->max_weight.p = reinterpret_cast<float*>(d + o_mw); b->ord_size.p = d + o_os; b->ord_maxw.p = d + o_om;
+    b->and_gstart.p = reinterpret_cast<uint32_t*>(d + o_and_gstart); b->and_item_begin.p = reinterpret_cast<uint32_t*>(d + o_and_begin);
+    b->un_gstart.p = reinterpret_cast<uint32_t*>(d + o_un_gstart); b->un_gterm.p = reinterpret_cast<uint32_t*>(d + o_un_gterm);
+    b->un_gquery.p = reinterpret_cast<uint32_t*>(d + o_un_gquery); b->un_gbase.p = reinterpret_cast<uint32_t*>(d + o_un_gbase);
+    b->un_item_begin.p = reinterpret_cast<uint32_t*>(d + o_un_begin); b->un_ub.p = reinterpret_cast<float*>(d + o_un_ub);
+    b->work_counter.p = reinterpret_cast<uint32_t*>(d + o_counter); b->stats.p = reinterpret_cast<unsigned long long*>(d + o_stats);
+    b->and_item_counts.p = reinterpret_cast<uint32_t*>(d + o_and_counts); b->and_item_sizes.p = reinterpret_cast<uint32_t*>(d + o_and_sizes);
+    b->un_item_sizes.p = reinterpret_cast<uint32_t*>(d + o_un_sizes); b->un_threshold.p = reinterpret_cast<uint32_t*>(d + o_un_thr);
+    b->out_fused.p = d + o_fused;
+    b->layout_outputs(MAX_K);
     CUDA_TRY(cudaEventCreate(&b->ev0)); CUDA_TRY(cudaEventCreate(&b->ev1));
-    if (trace_on()) fprintf(stderr, "[ds2i_gpu] prepare: per-query host work %.2f ms, work items + their uploads %.2f ms, remaining uploads %.2f ms\n",
-                            tp1 - tp0, tp2 - tp1, now_ms() - tp2);
+    // the staging memory is reused by the next batch of this index: the copy must have left it
+    CUDA_TRY(cudaStreamSynchronize(0));
+    if (trace_on()) fprintf(stderr, "[ds2i_gpu] prepare: per-query host work %.2f ms (%u threads), work items %.2f ms, allocation + upload of %zu bytes %.2f ms\n",
+                            tp1 - tp0, nthreads, tp2 - tp1, upload_bytes, now_ms() - tp2);
     *out = b.release();
     return DS2I_OK;
 }
@@ -514,7 +709,10 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     return DS2I_OK;
 }
 
-constexpr int AND_MIN_CTAS = 6;     // 24 resident warps per SM (<= 80 registers per thread)
+#ifndef DS2I_AND_MIN_CTAS
+#define DS2I_AND_MIN_CTAS 6
+#endif
+constexpr int AND_MIN_CTAS = DS2I_AND_MIN_CTAS;     // 6: 24 resident warps per SM (<= 80 registers per thread)
 
 template <int CODEC, bool RANKED, int MIN_CTAS = AND_MIN_CTAS>
 static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
@@ -553,10 +751,12 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
     switch (b->index->codec) {
         case CODEC_OPTPFOR:
             return launch_and_block<CODEC_OPTPFOR, RANKED>(b, db, k);
+#ifndef DS2I_DEV_FAST_BUILD
         case CODEC_VARINT: return launch_and_block<CODEC_VARINT, RANKED>(b, db, k);
         case CODEC_INTERPOLATIVE: return launch_and_block<CODEC_INTERPOLATIVE, RANKED>(b, db, k);
         case CODEC_QMX: return launch_and_block<CODEC_QMX, RANKED>(b, db, k);
         case CODEC_MIXED: return launch_and_block<CODEC_MIXED, RANKED>(b, db, k);
+#endif
     }
     return fail(DS2I_E_UNSUPPORTED, "unknown codec");
 }
@@ -594,6 +794,7 @@ template <int CODEC>
 static int launch_query_op(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32_t k) {
     switch (op) {
         case OP_AND: return launch_query<CODEC, OP_AND>(b, db, k);
+#ifndef DS2I_DEV_FAST_BUILD
         case OP_AND_FREQ: return launch_query<CODEC, OP_AND_FREQ>(b, db, k);
         case OP_OR: return launch_query<CODEC, OP_OR>(b, db, k);
         case OP_OR_FREQ: return launch_query<CODEC, OP_OR_FREQ>(b, db, k);
@@ -601,6 +802,7 @@ static int launch_query_op(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32
         case OP_WAND: return launch_query<CODEC, OP_WAND>(b, db, k);
         case OP_MAXSCORE: return launch_query<CODEC, OP_MAXSCORE>(b, db, k);
         case OP_RANKED_OR: return launch_query<CODEC, OP_RANKED_OR>(b, db, k);
+#endif
     }
     return fail(DS2I_E_ARG, "unknown operator");
 }
@@ -617,28 +819,30 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     if (ranked && (k < 1 || k > MAX_K)) return fail(DS2I_E_LIMIT, "k must be in 1.." + std::to_string(MAX_K));
     ds2i_gpu_index* ix = b->index;
     CUDA_TRY(cudaSetDevice(ix->device));
+    if (!ranked) k = 1;
+    b->layout_outputs(k);
     DevBatch db{};
     db.nq = b->nq; db.q_begin = b->q_begin.p; db.term = b->term.p; db.q_weight = b->q_weight.p;
     db.max_weight = b->max_weight.p; db.ord_size = b->ord_size.p; db.ord_maxw = b->ord_maxw.p;
     db.sched = b->sched.p; db.work_counter = b->work_counter.p; db.out_counts = b->out_counts.p;
     db.out_scores = b->out_scores.p; db.out_docids = b->out_docids.p; db.stats = b->stats.p;
-    CUDA_TRY(cudaMemsetAsync(b->stats.p, 0, 8 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, 4 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, 16 + 16 * 8));          // work counters and, right behind them, the statistics
     CUDA_TRY(cudaEventRecord(b->ev0));
     int rc = DS2I_OK;
     if (b->nq) {
         if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
-            if (!ranked) k = 1;
             rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k) : launch_and_block_codec<true>(b, db, k);
         }
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u)) {
             switch (ix->codec) {       // per-codec instances: smaller kernels, fewer instruction-cache misses
                 case CODEC_OPTPFOR: rc = launch_union_block<CODEC_OPTPFOR>(b, db, k); break;
+#ifndef DS2I_DEV_FAST_BUILD
                 case CODEC_VARINT: rc = launch_union_block<CODEC_VARINT>(b, db, k); break;
                 case CODEC_INTERPOLATIVE: rc = launch_union_block<CODEC_INTERPOLATIVE>(b, db, k); break;
                 case CODEC_QMX: rc = launch_union_block<CODEC_QMX>(b, db, k); break;
                 case CODEC_MIXED: rc = launch_union_block<CODEC_MIXED>(b, db, k); break;
+#endif
                 default: rc = fail(DS2I_E_UNSUPPORTED, "unknown codec");
             }
         }
@@ -647,12 +851,37 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
         b->launches += 1;
     }
     CUDA_TRY(cudaEventRecord(b->ev1));
+    b->last_k = ranked ? k : 0; b->last_ranked = ranked;
+    b->pending = true;
+    if (flags & DS2I_RUN_ASYNC) {                      // the caller orders later work behind stream 0 or calls ds2i_gpu_batch_wait
+        CUDA_TRY(cudaGetLastError());
+        if (out_elapsed_ms) *out_elapsed_ms = 0.f;
+        return DS2I_OK;
+    }
+    return ds2i_gpu_batch_wait(b, out_elapsed_ms);
+}
+
+extern "C" int ds2i_gpu_batch_wait(ds2i_gpu_batch* b, float* out_elapsed_ms) {
+    if (!b) return fail(DS2I_E_ARG, "null batch");
+    if (!b->pending) { if (out_elapsed_ms) *out_elapsed_ms = 0.f; return DS2I_OK; }
+    CUDA_TRY(cudaSetDevice(b->index->device));
     CUDA_TRY(cudaEventSynchronize(b->ev1));
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
     if (out_elapsed_ms) *out_elapsed_ms = ms;
-    b->last_k = ranked ? k : 0; b->last_ranked = ranked;
+    b->pending = false;
+#ifdef DS2I_NIN_HIST
+    {
+        unsigned long long h[32];
+        cudaMemcpyFromSymbol(h, g_hist, sizeof(h));
+        fprintf(stderr, "[hist]");
+        for (int i = 0; i < 32; ++i) fprintf(stderr, " %llu", h[i]);
+        fprintf(stderr, "\n");
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_hist, h, sizeof(h));
+    }
+#endif
     return DS2I_OK;
 }
 
@@ -690,13 +919,20 @@ extern "C" int ds2i_gpu_batch_device_results(ds2i_gpu_batch* b, void** d_counts,
     return DS2I_OK;
 }
 
+extern "C" int ds2i_gpu_batch_device_fused(ds2i_gpu_batch* b, void** d_fused, size_t* bytes) {
+    if (!b || !d_fused || !bytes) return fail(DS2I_E_ARG, "null argument");
+    *d_fused = b->out_fused.p;
+    *bytes = b->fused_bytes(b->last_ranked ? b->last_k : 0);
+    return DS2I_OK;
+}
+
 extern "C" int ds2i_gpu_batch_device_docids(ds2i_gpu_batch* b, void** d_docids) {
     if (!b || !d_docids) return fail(DS2I_E_ARG, "null argument");
     *d_docids = b->out_docids.p;
     return DS2I_OK;
 }
 
-extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { delete b; }
+extern "C" void ds2i_gpu_batch_free(ds2i_gpu_batch* b) { if (b) { device_scope ds(b->index->device); delete b; } }
 
 // ------------------------------------------------------------------------------------------------
 // Document-partitioned shards: fold the per-shard results of one query batch.  Shards hold disjoint
@@ -846,9 +1082,34 @@ __global__ void __launch_bounds__(SERIAL_WARPS * 32) decode_serial_blocks_kernel
     }
 }
 
+// sum of n u32 values as u64 (parity of a full-scale decode without moving 3.4 GB to the host: "a checksum of checksums")
+__global__ void __launch_bounds__(256) sum_u32_kernel(const uint32_t* v, uint64_t n, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) acc += v[i];
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+static int decode_lists_impl(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms, const uint64_t* out_offsets, uint32_t* out_docs,
+                             uint32_t* out_freqs, uint64_t* out_sums /* [2] or null */, float* out_elapsed_ms);
+
 extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms,
                                      const uint64_t* out_offsets, uint32_t* out_docs, uint32_t* out_freqs,
                                      float* out_elapsed_ms) {
+    return decode_lists_impl(ix, terms, nterms, out_offsets, out_docs, out_freqs, nullptr, out_elapsed_ms);
+}
+
+extern "C" int ds2i_gpu_decode_lists_checksum(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms, const uint64_t* out_offsets,
+                                              uint64_t* out_sum_docids, uint64_t* out_sum_freqs, float* out_elapsed_ms) {
+    if (!out_sum_docids || !out_sum_freqs) return fail(DS2I_E_ARG, "null argument");
+    uint64_t sums[2] = {0, 0};
+    int rc = decode_lists_impl(ix, terms, nterms, out_offsets, nullptr, nullptr, sums, out_elapsed_ms);
+    *out_sum_docids = sums[0]; *out_sum_freqs = sums[1];
+    return rc;
+}
+
+static int decode_lists_impl(ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms, const uint64_t* out_offsets, uint32_t* out_docs,
+                             uint32_t* out_freqs, uint64_t* out_sums, float* out_elapsed_ms) {
     if (!ix || (!terms && nterms) || !out_offsets) return fail(DS2I_E_ARG, "null argument");
     if (nterms > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many lists");
     CUDA_TRY(cudaSetDevice(ix->device));
@@ -867,12 +1128,15 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
     CUDA_TRY(d_docs.alloc(total)); CUDA_TRY(d_freqs.alloc(total));
     PefDecodeItem* pef_items = nullptr;
     uint32_t pef_nitems = 0;
+    cuda_free_guard pef_items_guard;
     if (ix->kind == KIND_PEF && nterms && total) {
         int prc = pef_decode_prepare(*ix->pef, terms, uint32_t(nterms), &pef_items, &pef_nitems, g_last_error);
+        pef_items_guard.p = pef_items;
         if (prc) return prc;
     }
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    cuda_event ev0, ev1;
+    CUDA_TRY(ev0.create()); CUDA_TRY(ev1.create());
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     CUDA_TRY(cudaEventRecord(e0));
     int rc = DS2I_OK;
     if (nterms && total) {
@@ -901,12 +1165,22 @@ extern "C" int ds2i_gpu_decode_lists(ds2i_gpu_index* ix, const uint32_t* terms, 
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (pef_items) cudaFree(pef_items);
     if (rc != DS2I_OK) return rc;
     if (out_elapsed_ms) *out_elapsed_ms = ms;
     if (total && out_docs) CUDA_TRY(cudaMemcpy(out_docs, d_docs.p, total * 4, cudaMemcpyDeviceToHost));
     if (total && out_freqs) CUDA_TRY(cudaMemcpy(out_freqs, d_freqs.p, total * 4, cudaMemcpyDeviceToHost));
+    if (out_sums) {
+        dev_buf<unsigned long long> d_sums;
+        CUDA_TRY(d_sums.alloc(2));
+        CUDA_TRY(cudaMemsetAsync(d_sums.p, 0, 16));
+        if (total) {
+            sum_u32_kernel<<<ix->sm_count * 8, 256>>>(d_docs.p, total, d_sums.p);
+            sum_u32_kernel<<<ix->sm_count * 8, 256>>>(d_freqs.p, total, d_sums.p + 1);
+        }
+        unsigned long long h[2];
+        CUDA_TRY(cudaMemcpy(h, d_sums.p, 16, cudaMemcpyDeviceToHost));
+        out_sums[0] = h[0]; out_sums[1] = h[1];
+    }
     return DS2I_OK;
 }
 
@@ -966,8 +1240,9 @@ extern "C" int ds2i_gpu_next_geq_batch(ds2i_gpu_index* ix, const uint32_t* terms
     CUDA_TRY(d_terms.upload(tv)); CUDA_TRY(d_bounds.upload(bv)); CUDA_TRY(d_offs.upload(ov));
     CUDA_TRY(d_docids.alloc(total)); CUDA_TRY(d_freqs.alloc(total)); CUDA_TRY(d_counter.alloc(1));
     CUDA_TRY(cudaMemset(d_counter.p, 0, 4));
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    cuda_event ev0, ev1;
+    CUDA_TRY(ev0.create()); CUDA_TRY(ev1.create());
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     CUDA_TRY(cudaEventRecord(e0));
     int rc = DS2I_OK;
     if (nlists) {
@@ -984,10 +1259,205 @@ extern "C" int ds2i_gpu_next_geq_batch(ds2i_gpu_index* ix, const uint32_t* terms
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (rc != DS2I_OK) return rc;
     if (out_elapsed_ms) *out_elapsed_ms = ms;
     if (total && out_docids) CUDA_TRY(cudaMemcpy(out_docids, d_docids.p, total * 8, cudaMemcpyDeviceToHost));
     if (total && out_freqs) CUDA_TRY(cudaMemcpy(out_freqs, d_freqs.p, total * 8, cudaMemcpyDeviceToHost));
+    return DS2I_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs behind the C ABI: one process, the index (and wand data) replicated on every device, the
+// query batch cut into cost-balanced shards, one host thread per GPU (the reference's own parallel driver deals query i to
+// thread i % n the same way, profile_queries.cpp:21-39), per-shard results gathered to the first device over NCCL
+// (ncclCommInitAll; NVLink / NVSwitch) and copied to the caller's host buffers in one D2H transfer.
+struct nccl_api {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        // a process that already holds an NCCL (e.g. PyTorch's bundled one) gets that copy: same soname
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("NCCL not found: ") + dlerror(); return false; }
+        auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) err = std::string("NCCL symbol missing: ") + n; return p; };
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+        Send = reinterpret_cast<decltype(Send)>(sym("ncclSend"));
+        Recv = reinterpret_cast<decltype(Recv)>(sym("ncclRecv"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Send && Recv && GetErrorString;
+    }
+};
+static nccl_api g_nccl;
+static std::mutex g_nccl_mu;
+
+struct ds2i_gpu_group {
+    std::vector<int> devices;
+    std::vector<ds2i_gpu_index*> indexes;
+    std::vector<ds2i_gpu_wand*> wands;          // empty when the group was opened without wand data
+    std::vector<ncclComm_t> comms;              // empty for a single device
+    dev_buf<uint8_t> gathered;                  // on devices[0]: the fused results of every shard, back to back
+    pinned_arena host;                          // D2H staging of the gathered results
+    ~ds2i_gpu_group() {
+        for (ncclComm_t c : comms) if (c) g_nccl.CommDestroy(c);
+        for (auto* w : wands) ds2i_gpu_wand_close(w);
+        for (auto* ix : indexes) ds2i_gpu_index_close(ix);
+    }
+};
+
+extern "C" int ds2i_gpu_group_open(const char* index_path, const char* index_type, const char* wand_path, const int* devices, int ndevices,
+                                   ds2i_gpu_group** out) {
+    if (!index_path || !index_type || !out || ndevices < 1) return fail(DS2I_E_ARG, "bad argument");
+    int have = 0;
+    CUDA_TRY(cudaGetDeviceCount(&have));
+    std::unique_ptr<ds2i_gpu_group> g(new ds2i_gpu_group);
+    for (int i = 0; i < ndevices; ++i) {
+        const int dev = devices ? devices[i] : i;
+        if (dev < 0 || dev >= have) return fail(DS2I_E_ARG, "device " + std::to_string(dev) + " does not exist (" + std::to_string(have) + " visible)");
+        if (std::find(g->devices.begin(), g->devices.end(), dev) != g->devices.end()) return fail(DS2I_E_ARG, "device listed twice");
+        g->devices.push_back(dev);
+    }
+    // replicas are loaded concurrently, one thread per device (the file is read through the page cache once)
+    g->indexes.assign(ndevices, nullptr);
+    if (wand_path) g->wands.assign(ndevices, nullptr);
+    std::vector<int> rcs(ndevices, DS2I_OK);
+    std::vector<std::string> errs(ndevices);
+    {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < ndevices; ++i)
+            pool.emplace_back([&, i] {
+                rcs[i] = ds2i_gpu_index_open_file(index_path, index_type, g->devices[i], &g->indexes[i]);
+                if (rcs[i] == DS2I_OK && wand_path) rcs[i] = ds2i_gpu_wand_open_file(wand_path, g->devices[i], &g->wands[i]);
+                if (rcs[i] != DS2I_OK) errs[i] = ds2i_gpu_last_error();
+            });
+        for (auto& t : pool) t.join();
+    }
+    for (int i = 0; i < ndevices; ++i) if (rcs[i] != DS2I_OK) return fail(rcs[i], errs[i]);
+    if (ndevices > 1) {
+        std::lock_guard<std::mutex> lock(g_nccl_mu);
+        std::string err;
+        if (!g_nccl.load(err)) return fail(DS2I_E_UNSUPPORTED, err);
+        g->comms.assign(ndevices, nullptr);
+        ncclResult_t r = g_nccl.CommInitAll(g->comms.data(), ndevices, g->devices.data());
+        if (r != ncclSuccess) { g->comms.clear(); return fail(DS2I_E_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r)); }
+    }
+    *out = g.release();
+    return DS2I_OK;
+}
+
+extern "C" void ds2i_gpu_group_close(ds2i_gpu_group* g) { delete g; }
+extern "C" int ds2i_gpu_group_size(const ds2i_gpu_group* g) { return g ? int(g->devices.size()) : 0; }
+extern "C" ds2i_gpu_index* ds2i_gpu_group_index(ds2i_gpu_group* g, int i) { return g && i >= 0 && size_t(i) < g->indexes.size() ? g->indexes[i] : nullptr; }
+
+extern "C" int ds2i_gpu_group_query_batch(ds2i_gpu_group* g, int op, uint32_t k, const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
+                                          uint64_t* out_counts, float* out_scores, uint32_t* out_docids, float* out_elapsed_ms) {
+    if (!g || !query_offsets || (!terms && nq && query_offsets[nq])) return fail(DS2I_E_ARG, "null argument");
+    if (op < 0 || op > OP_RANKED_OR) return fail(DS2I_E_ARG, "unknown operator");
+    const bool ranked = op >= OP_RANKED_AND;
+    if (ranked && g->wands.empty()) return fail(DS2I_E_ARG, "ranked operators need wand data");
+    if (ranked && (k < 1 || k > MAX_K)) return fail(DS2I_E_LIMIT, "k must be in 1.." + std::to_string(MAX_K));
+    const size_t G = g->devices.size();
+    const uint32_t kk = ranked ? k : 0;
+
+    // cost-balanced shards: queries sorted by the postings of their lists, dealt round-robin (shard sizes differ by <= 1)
+    std::vector<uint32_t> order(nq);
+    {
+        ds2i_gpu_index* ix0 = g->indexes[0];
+        std::vector<uint64_t> cost(nq, 0);
+        for (size_t q = 0; q < nq; ++q) {
+            if (query_offsets[q + 1] < query_offsets[q]) return fail(DS2I_E_ARG, "query_offsets not monotone");
+            for (uint64_t j = query_offsets[q]; j < query_offsets[q + 1]; ++j) {
+                if (terms[j] >= ix0->size) return fail(DS2I_E_ARG, "term id out of range in query " + std::to_string(q));
+                cost[q] += list_size_of(ix0, terms[j]);
+            }
+        }
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+    }
+    std::vector<std::vector<uint32_t>> shard_q(G), shard_terms(G);
+    std::vector<std::vector<uint64_t>> shard_offs(G);
+    for (size_t s = 0; s < G; ++s) {
+        shard_offs[s].push_back(0);
+        for (size_t p = s; p < nq; p += G) {
+            const uint32_t q = order[p];
+            shard_q[s].push_back(q);
+            shard_terms[s].insert(shard_terms[s].end(), terms + query_offsets[q], terms + query_offsets[q + 1]);
+            shard_offs[s].push_back(shard_terms[s].size());
+        }
+    }
+
+    // one host thread per GPU: prepare + run (results stay in the shard's fused device buffer)
+    std::vector<ds2i_gpu_batch*> batches(G, nullptr);
+    std::vector<int> rcs(G, DS2I_OK);
+    std::vector<std::string> errs(G);
+    std::vector<float> kernel_ms(G, 0.f);
+    const unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE) ? 2u : 0u;
+    auto work = [&](size_t s) {
+        static const uint32_t no_terms = 0;
+        const uint32_t* tp = shard_terms[s].empty() ? &no_terms : shard_terms[s].data();
+        rcs[s] = batch_prepare_impl(g->indexes[s], g->wands.empty() ? nullptr : g->wands[s], tp, shard_offs[s].data(), shard_q[s].size(), which, &batches[s]);
+        if (rcs[s] == DS2I_OK) rcs[s] = ds2i_gpu_batch_run_ex(batches[s], op, k, 0u, &kernel_ms[s]);
+        if (rcs[s] != DS2I_OK) errs[s] = ds2i_gpu_last_error();
+    };
+    {
+        std::vector<std::thread> pool;
+        for (size_t s = 1; s < G; ++s) pool.emplace_back(work, s);
+        work(0);
+        for (auto& t : pool) t.join();
+    }
+    struct batch_guard { std::vector<ds2i_gpu_batch*>& v; ~batch_guard() { for (auto* b : v) ds2i_gpu_batch_free(b); } } guard{batches};
+    for (size_t s = 0; s < G; ++s) if (rcs[s] != DS2I_OK) return fail(rcs[s], errs[s]);
+
+    // gather the fused per-shard results on the first device: ncclSend from every other GPU, ncclRecv on the first, one group
+    std::vector<size_t> off(G + 1, 0);
+    for (size_t s = 0; s < G; ++s) off[s + 1] = off[s] + ((batches[s]->fused_bytes(kk) + 15) & ~size_t(15));
+    const uint8_t* d_all = nullptr;
+    CUDA_TRY(cudaSetDevice(g->devices[0]));
+    if (G == 1) {
+        d_all = batches[0]->out_fused.p;
+    } else {
+        CUDA_TRY(g->gathered.alloc(off[G]));
+        CUDA_TRY(cudaMemcpyAsync(g->gathered.p, batches[0]->out_fused.p, batches[0]->fused_bytes(kk), cudaMemcpyDeviceToDevice, 0));
+        ncclResult_t r = g_nccl.GroupStart();
+        for (size_t s = 1; s < G && r == ncclSuccess; ++s) {
+            const size_t bytes = batches[s]->fused_bytes(kk);
+            if (!bytes) continue;
+            r = g_nccl.Recv(g->gathered.p + off[s], bytes, ncclUint8, int(s), g->comms[0], 0);
+            if (r == ncclSuccess) r = g_nccl.Send(batches[s]->out_fused.p, bytes, ncclUint8, 0, g->comms[s], 0);
+        }
+        ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) return fail(DS2I_E_CUDA, std::string("NCCL gather: ") + g_nccl.GetErrorString(r));
+        CUDA_TRY(cudaSetDevice(g->devices[0]));
+        d_all = g->gathered.p;
+    }
+    CUDA_TRY(g->host.reserve(std::max<size_t>(off[G], 16)));
+    if (off[G]) CUDA_TRY(cudaMemcpyAsync(g->host.p, d_all, G == 1 ? batches[0]->fused_bytes(kk) : off[G], cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    for (size_t s = 1; s < G; ++s) { CUDA_TRY(cudaSetDevice(g->devices[s])); CUDA_TRY(cudaStreamSynchronize(0)); }     // the sends have left the shard buffers
+
+    // rows back into the caller's query order
+    for (size_t s = 0; s < G; ++s) {
+        const size_t n = shard_q[s].size();
+        const uint8_t* base = g->host.p + off[s];
+        const uint64_t* c = reinterpret_cast<const uint64_t*>(base);
+        const float* sc = reinterpret_cast<const float*>(base + n * 8);
+        const uint32_t* di = reinterpret_cast<const uint32_t*>(base + n * 8 + n * kk * 4);
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t q = shard_q[s][i];
+            if (out_counts) out_counts[q] = c[i];
+            if (ranked && out_scores) memcpy(out_scores + size_t(q) * k, sc + i * k, size_t(k) * 4);
+            if (ranked && out_docids) memcpy(out_docids + size_t(q) * k, di + i * k, size_t(k) * 4);
+        }
+    }
+    if (out_elapsed_ms) *out_elapsed_ms = *std::max_element(kernel_ms.begin(), kernel_ms.end());
     return DS2I_OK;
 }

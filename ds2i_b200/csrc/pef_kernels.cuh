@@ -453,13 +453,13 @@ struct PefIndexHost {
     static int upload(PefSeqHost& s, bitvec_view const& bv, std::string& err) {
         size_t words = size_t(bv.nwords) + 64;       // zero tail: scans read 32 words per step
         if (cudaMalloc(reinterpret_cast<void**>(&s.d_bits), words * 8) != cudaSuccess) { err = "cudaMalloc failed (bit vector)"; return -3; }
-        cudaMemset(s.d_bits, 0, words * 8);
+        if (cudaMemset(s.d_bits, 0, words * 8) != cudaSuccess) { err = "cudaMemset failed (bit vector)"; return -3; }
         if (bv.nwords && cudaMemcpy(s.d_bits, bv.raw, size_t(bv.nwords) * 8, cudaMemcpyHostToDevice) != cudaSuccess) { err = "H2D copy failed"; return -3; }
         if (cudaMalloc(reinterpret_cast<void**>(&s.d_lists), std::max<size_t>(1, s.lists.size()) * sizeof(PefListDir)) != cudaSuccess ||
             cudaMalloc(reinterpret_cast<void**>(&s.d_parts), (s.parts.size() + 64) * sizeof(PefPart)) != cudaSuccess) { err = "cudaMalloc failed (directory)"; return -3; }
-        cudaMemset(s.d_parts, 0, (s.parts.size() + 64) * sizeof(PefPart));
-        cudaMemcpy(s.d_lists, s.lists.data(), s.lists.size() * sizeof(PefListDir), cudaMemcpyHostToDevice);
-        cudaMemcpy(s.d_parts, s.parts.data(), s.parts.size() * sizeof(PefPart), cudaMemcpyHostToDevice);
+        if (cudaMemset(s.d_parts, 0, (s.parts.size() + 64) * sizeof(PefPart)) != cudaSuccess ||
+            cudaMemcpy(s.d_lists, s.lists.data(), s.lists.size() * sizeof(PefListDir), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(s.d_parts, s.parts.data(), s.parts.size() * sizeof(PefPart), cudaMemcpyHostToDevice) != cudaSuccess) { err = "H2D copy failed (directory)"; return -3; }
         s.device_bytes = words * 8 + s.lists.size() * sizeof(PefListDir) + s.parts.size() * sizeof(PefPart);
         return 0;
     }
@@ -538,6 +538,7 @@ static int pef_launch_op(PefIndexHost& ix, DevWand wand, DevBatch const& db, uin
 inline int pef_launch_query(PefIndexHost& ix, DevWand wand, DevBatch const& db, int op, uint32_t k, int max_terms, int sm_count, std::string& err) {
     switch (op) {
         case OP_AND: return pef_launch_op<OP_AND>(ix, wand, db, k, max_terms, sm_count, err);
+#ifndef DS2I_DEV_FAST_BUILD      // kernel-experiment builds instantiate one operator only (seconds instead of minutes)
         case OP_AND_FREQ: return pef_launch_op<OP_AND_FREQ>(ix, wand, db, k, max_terms, sm_count, err);
         case OP_OR: return pef_launch_op<OP_OR>(ix, wand, db, k, max_terms, sm_count, err);
         case OP_OR_FREQ: return pef_launch_op<OP_OR_FREQ>(ix, wand, db, k, max_terms, sm_count, err);
@@ -545,6 +546,7 @@ inline int pef_launch_query(PefIndexHost& ix, DevWand wand, DevBatch const& db, 
         case OP_WAND: return pef_launch_op<OP_WAND>(ix, wand, db, k, max_terms, sm_count, err);
         case OP_MAXSCORE: return pef_launch_op<OP_MAXSCORE>(ix, wand, db, k, max_terms, sm_count, err);
         case OP_RANKED_OR: return pef_launch_op<OP_RANKED_OR>(ix, wand, db, k, max_terms, sm_count, err);
+#endif
     }
     err = "unknown operator";
     return -1;
@@ -568,7 +570,7 @@ inline int pef_decode_prepare(PefIndexHost& ix, const uint32_t* h_terms, uint32_
     *d_items = nullptr;
     if (items.empty()) return 0;
     if (cudaMalloc(reinterpret_cast<void**>(d_items), items.size() * sizeof(PefDecodeItem)) != cudaSuccess) { err = "cudaMalloc failed"; return -3; }
-    cudaMemcpy(*d_items, items.data(), items.size() * sizeof(PefDecodeItem), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(*d_items, items.data(), items.size() * sizeof(PefDecodeItem), cudaMemcpyHostToDevice) != cudaSuccess) { err = "H2D copy failed"; return -3; }
     return 0;
 }
 

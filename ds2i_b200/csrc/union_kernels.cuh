@@ -176,10 +176,17 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
         const uint32_t nt = batch.q_begin[q + 1] - t0;
         const uint32_t e = __ldg(job.gterm + g) - t0;
         const volatile uint32_t* thr_g = job.query_threshold + q;
+        // other warps raise the shared threshold concurrently: ONE lane reads it and broadcasts, so the value that steers
+        // warp-uniform control flow (continue / stop / bar()) is the same in all 32 lanes
+        auto read_threshold = [&]() -> float {
+            uint32_t t = 0;
+            if (lane == 0) t = *thr_g;
+            return __uint_as_float(__shfl_sync(FULL, t, 0));
+        };
 
         TopKShared topk;
         topk.init(k);
-        topk.floor_ = __uint_as_float(*thr_g);
+        topk.floor_ = read_threshold();
         const float ub_e = __ldg(job.ub + t0 + e) * INFLATE;
         if (!(ub_e > topk.floor_)) {           // list e is non-essential already: nothing it owns can enter
             if (lane == 0) job.item_sizes[rslot] = 0;
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
             }
             for (uint32_t b0 = c0; b0 < c1; ++b0) {
                 // refresh the shared floor (queries.hpp:568-574: the non-essential prefix only grows)
-                topk.floor_ = fmaxf(topk.floor_, __uint_as_float(*thr_g));
+                topk.floor_ = fmaxf(topk.floor_, read_threshold());
                 if (!(ub_e > topk.bar())) { stop = true; break; }
                 {
                     const uint32_t l = b0 - c0;
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (alive & (1u << j)) score[j] = qw_e * doc_term_weight(f0[j] + 1u, norm_len[j]);
-                        c.c_scored += __reduce_add_sync(FULL, __popc(alive));
+                        DS2I_STAT(c.c_scored += __reduce_add_sync(FULL, __popc(alive));)
                         continue;
                     }
                     if (i < e) {

@@ -53,6 +53,7 @@ enum {
 
 const char* ds2i_gpu_last_error(void);
 int ds2i_gpu_op_from_name(const char* name);          /* "ranked_and" -> DS2I_OP_RANKED_AND; <0 if unknown */
+int ds2i_gpu_index_type_known(const char* index_type); /* 1 for the entries of DS2I_INDEX_TYPES (index_types.hpp:41), else 0 */
 
 /* ---- Index: replaces succinct::mapper::map(index, mapped_file) + the Index concept ------------
  * (queries.cpp:73-77; block_freq_index.hpp:73-134; freq_index.hpp:106-243).
@@ -107,7 +108,12 @@ int ds2i_gpu_batch_run(ds2i_gpu_batch*, int op, uint32_t k, float* out_elapsed_m
  * dynamic-pruning kernel (same top-k; a score may differ from the reference in the last bit because
  * the BM25 summation order follows the pruning state — within 1e-5 relative). */
 #define DS2I_RUN_FAITHFUL 1u
+/* DS2I_RUN_ASYNC: launch and return without waiting; the work is ordered on the device's default stream (stream 0), so a
+ * caller may enqueue a collective or a copy behind it, or call ds2i_gpu_batch_wait (which also reports the CUDA-event time).
+ * The fetch / stats calls copy on the same stream and therefore see the finished results either way. */
+#define DS2I_RUN_ASYNC 2u
 int ds2i_gpu_batch_run_ex(ds2i_gpu_batch*, int op, uint32_t k, uint32_t flags, float* out_elapsed_ms);
+int ds2i_gpu_batch_wait(ds2i_gpu_batch*, float* out_elapsed_ms);
 int ds2i_gpu_batch_fetch(ds2i_gpu_batch*, uint64_t* out_counts, float* out_scores);   /* D2H of the last run */
 /* docids of the scores of the last (ranked) run, nq * k, same layout as out_scores, 0xffffffff where a query has
  * fewer than k results.  The reference's topk_queue keeps scores only (queries.hpp:157-172); a caller that has to
@@ -121,6 +127,9 @@ int ds2i_gpu_batch_stats(ds2i_gpu_batch*, uint64_t out_stats[8]);
  * hand them to a collective (NCCL gather of per-shard top-k) without a host round trip. */
 int ds2i_gpu_batch_device_results(ds2i_gpu_batch*, void** d_counts, void** d_scores);
 int ds2i_gpu_batch_device_docids(ds2i_gpu_batch*, void** d_docids);      /* device pointer to the nq * k docids of the last ranked run */
+/* The three result arrays of the last run are ONE contiguous device buffer, [counts: nq u64][scores: nq*k f32][docids: nq*k u32]
+ * (unranked operators: counts only), so that a single collective or copy moves a shard's results. */
+int ds2i_gpu_batch_device_fused(ds2i_gpu_batch*, void** d_fused, size_t* bytes);
 
 /* Document-partitioned shards.  Every shard evaluated the same nq queries; row (s * nq + q) of the
  * DEVICE arrays d_counts / d_scores / d_docids (docids already global) holds shard s's result for query q — the layout an
@@ -130,6 +139,23 @@ int ds2i_gpu_merge_shards(const uint64_t* d_counts, const float* d_scores, const
                           uint32_t k, int ranked, uint64_t* d_out_counts, float* d_out_scores, uint32_t* d_out_docids);
 void ds2i_gpu_batch_free(ds2i_gpu_batch*);
 
+/* ---- Several GPUs of one process -------------------------------------------------------------------
+ * The reference's only parallel driver deals query i to thread i % n, one operator copy per thread, index shared
+ * (profile_queries.cpp:21-39).  Here a group holds one replica of the index (and wand data) per device; a batch is cut into
+ * cost-balanced shards (queries sorted by the postings of their lists, dealt round-robin), every GPU evaluates its shard
+ * concurrently (one host thread per device), the fused per-shard results are gathered on the first device over NCCL
+ * (ncclCommInitAll communicators, ncclSend / ncclRecv in one group; libnccl is dlopen'ed on first use) and reach the caller's
+ * host buffers in one D2H copy, in the caller's query order.  devices == NULL means 0 .. ndevices-1; wand_path may be NULL
+ * for and / or.  out_elapsed_ms is the largest per-GPU CUDA-event time. */
+typedef struct ds2i_gpu_group ds2i_gpu_group;
+int ds2i_gpu_group_open(const char* index_path, const char* index_type, const char* wand_path, const int* devices, int ndevices,
+                        ds2i_gpu_group** out);
+void ds2i_gpu_group_close(ds2i_gpu_group*);
+int ds2i_gpu_group_size(const ds2i_gpu_group*);
+ds2i_gpu_index* ds2i_gpu_group_index(ds2i_gpu_group*, int i);            /* the replica on the i-th device (owned by the group) */
+int ds2i_gpu_group_query_batch(ds2i_gpu_group*, int op, uint32_t k, const uint32_t* terms, const uint64_t* query_offsets, size_t nq,
+                               uint64_t* out_counts, float* out_scores, uint32_t* out_docids, float* out_elapsed_ms);
+
 /* ---- Enumerator-level entry points (document_enumerator, block_posting_list.hpp:105-186) -------
  * Full sequential decode of whole lists: for each term, docid()/freq() of every posting as
  * next() would deliver them.  out_offsets[i] (nterms+1 entries, in postings) says where list i
@@ -137,6 +163,11 @@ void ds2i_gpu_batch_free(ds2i_gpu_batch*);
 int ds2i_gpu_decode_lists(ds2i_gpu_index*, const uint32_t* terms, size_t nterms,
                           const uint64_t* out_offsets, uint32_t* out_docs, uint32_t* out_freqs,
                           float* out_elapsed_ms);
+/* The same decode with the outputs left in HBM and reduced there: sum of every docid() and of every freq() over all postings
+ * of the listed terms — the checksum a full-scale decode (hundreds of millions of postings) is compared on, next to a
+ * bit-exact comparison of sampled lists through ds2i_gpu_decode_lists. */
+int ds2i_gpu_decode_lists_checksum(ds2i_gpu_index*, const uint32_t* terms, size_t nterms, const uint64_t* out_offsets,
+                                   uint64_t* out_sum_docids, uint64_t* out_sum_freqs, float* out_elapsed_ms);
 /* next_geq sweeps: list i = index[terms[i]] is opened (positioned on its first posting), then
  * next_geq(bounds[j]) is applied for j in bound_offsets[i]..bound_offsets[i+1] (non-decreasing
  * bounds); out_docids[j] = docid() after the call, out_freqs[j] = freq() (0 past the end). */

@@ -68,6 +68,7 @@ public:
     gpu_index(const void* bytes, size_t n, const char* index_type, int device = 0) : m_h(nullptr) {
         check(ds2i_gpu_index_open(bytes, n, index_type, device, &m_h));
     }
+    explicit gpu_index(ds2i_gpu_index* adopted) : m_h(adopted) {}      // takes ownership of a handle opened through the C ABI
     ~gpu_index() { ds2i_gpu_index_close(m_h); }
     gpu_index(gpu_index const&) = delete;
     gpu_index& operator=(gpu_index const&) = delete;
@@ -134,6 +135,39 @@ inline query_batch_result run_batch(gpu_index const& index, gpu_wand_data const*
     r.docids.assign(queries.size() * k, 0xffffffffu);
     check(ds2i_gpu_query_batch_docids(index.handle(), wdata ? wdata->handle() : nullptr, op, k, terms.data(), offsets.data(), queries.size(),
                                       r.counts.data(), r.scores.data(), r.docids.data(), &r.elapsed_ms));
+    return r;
+}
+
+// the index (and wand data) replicated over several GPUs of this process; a batch is sharded over them (ds2i_gpu_group_*)
+class gpu_group {
+public:
+    gpu_group(const char* index_path, const char* index_type, const char* wand_path, int ngpus) : m_h(nullptr) {
+        check(ds2i_gpu_group_open(index_path, index_type, wand_path, nullptr, ngpus, &m_h));
+    }
+    explicit gpu_group(ds2i_gpu_group* adopted) : m_h(adopted) {}
+    ~gpu_group() { ds2i_gpu_group_close(m_h); }
+    gpu_group(gpu_group const&) = delete;
+    gpu_group& operator=(gpu_group const&) = delete;
+    int size() const { return ds2i_gpu_group_size(m_h); }
+    ds2i_gpu_group* handle() const { return m_h; }
+private:
+    ds2i_gpu_group* m_h;
+};
+
+inline query_batch_result run_batch(gpu_group const& group, int op, std::vector<term_id_vec> const& queries, uint32_t k = 10) {
+    std::vector<uint32_t> terms;
+    std::vector<uint64_t> offsets(queries.size() + 1, 0);
+    for (size_t i = 0; i < queries.size(); ++i) {
+        terms.insert(terms.end(), queries[i].begin(), queries[i].end());
+        offsets[i + 1] = terms.size();
+    }
+    query_batch_result r;
+    r.k = k;
+    r.counts.resize(queries.size());
+    r.scores.assign(queries.size() * k, 0.f);
+    r.docids.assign(queries.size() * k, 0xffffffffu);
+    check(ds2i_gpu_group_query_batch(group.handle(), op, k, terms.data(), offsets.data(), queries.size(), r.counts.data(), r.scores.data(),
+                                     r.docids.data(), &r.elapsed_ms));
     return r;
 }
 

@@ -10,6 +10,9 @@
 //   ref_tool nextgeq <type> <index> <spec.bin> <out.bin>
 //   ref_tool bench   <type> <index> <wand> <queries> <op> <threads> [max_queries] [passes]
 //   ref_tool profile <type> <index> <wand> <queries> <op> <out.bin> [max_queries]   (block types only)
+//   ref_tool scan    <type> <index> <terms.txt | all | first:N> <threads> [passes]   timed next()/docid()/freq() scan of whole lists
+//                    (list i -> thread i % n, profile_queries.cpp:21-39); prints postings/s and sum(docid) / sum(freq) checksums
+//   ref_tool geqbench <type> <index> <spec.bin> <threads> [passes]   timed next_geq sweeps (same spec as nextgeq)
 //   ref_tool info    <type> <index>
 //   ref_tool mkmixed block_optpfor <index> <out block_mixed index> [seed]   block types drawn per block; the reference's
 //                    own transformation path (optimal_hybrid_index.cpp:266-292) writes the block_mixed index
@@ -310,6 +313,106 @@ int cmd_profile(int argc, char** argv)
     return 0;
 }
 
+// "decode baseline ... 1 thread and all cores": the reference's own sequential enumeration of whole lists
+template <typename Index>
+int cmd_scan(int argc, char** argv)
+{
+    // argv: scan type index spec threads [passes]
+    Index index;
+    boost::iostreams::mapped_file_source m(argv[3]);
+    succinct::mapper::map(index, m);
+    std::string spec = argv[4];
+    size_t n_threads = std::stoull(argv[5]);
+    if (!n_threads) n_threads = std::max<size_t>(1, std::thread::hardware_concurrency());
+    size_t passes = argc > 6 ? std::stoull(argv[6]) : 1;
+    std::vector<uint64_t> terms;
+    if (spec == "all") { for (uint64_t t = 0; t < index.size(); ++t) terms.push_back(t); }
+    else if (spec.compare(0, 6, "first:") == 0) { uint64_t n = std::min<uint64_t>(index.size(), std::stoull(spec.substr(6))); for (uint64_t t = 0; t < n; ++t) terms.push_back(t); }
+    else { std::ifstream tin(spec); uint64_t t; while (tin >> t) terms.push_back(t); }
+    for (auto t : terms) index.warmup(t);
+    double best = 1e300;
+    uint64_t postings = 0, sum_docs = 0, sum_freqs = 0;
+    std::string pass_list;
+    for (size_t pass = 0; pass < passes; ++pass) {
+        std::vector<uint64_t> n(n_threads, 0), sd(n_threads, 0), sf(n_threads, 0);
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> threads;
+        for (size_t t = 0; t < n_threads; ++t) {
+            threads.emplace_back([&, t]() {
+                uint64_t cnt = 0, a = 0, b = 0;
+                for (size_t i = t; i < terms.size(); i += n_threads) {
+                    auto e = index[terms[i]];
+                    uint64_t len = e.size();
+                    for (uint64_t j = 0; j < len; ++j) { a += e.docid(); b += e.freq(); e.next(); }
+                    cnt += len;
+                }
+                n[t] = cnt; sd[t] = a; sf[t] = b;
+            });
+        }
+        for (auto& th : threads) th.join();
+        double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        best = std::min(best, secs);
+        char tmp[64]; snprintf(tmp, sizeof tmp, "%s%.6f", pass ? ", " : "", secs); pass_list += tmp;
+        postings = sum_docs = sum_freqs = 0;
+        for (size_t t = 0; t < n_threads; ++t) { postings += n[t]; sum_docs += sd[t]; sum_freqs += sf[t]; }
+    }
+    printf("{\"type\": \"%s\", \"lists\": %zu, \"threads\": %zu, \"postings\": %llu, \"seconds\": %.6f, \"postings_per_s\": %.1f, "
+           "\"sum_docids\": %llu, \"sum_freqs\": %llu, \"pass_seconds\": [%s]}\n", argv[2], terms.size(), n_threads,
+           (unsigned long long)postings, best, postings / best, (unsigned long long)sum_docs, (unsigned long long)sum_freqs, pass_list.c_str());
+    return 0;
+}
+
+// timed next_geq sweeps over the lists of a spec file (the format of `nextgeq`); list i -> thread i % n
+template <typename Index>
+int cmd_geqbench(int argc, char** argv)
+{
+    Index index;
+    boost::iostreams::mapped_file_source m(argv[3]);
+    succinct::mapper::map(index, m);
+    FILE* in = fopen(argv[4], "rb");
+    if (!in) { perror("spec"); return 1; }
+    size_t n_threads = std::stoull(argv[5]);
+    if (!n_threads) n_threads = std::max<size_t>(1, std::thread::hardware_concurrency());
+    size_t passes = argc > 6 ? std::stoull(argv[6]) : 1;
+    uint64_t nl;
+    if (fread(&nl, 8, 1, in) != 1) return 1;
+    std::vector<uint64_t> terms(nl);
+    std::vector<std::vector<uint64_t>> bounds(nl);
+    uint64_t calls = 0;
+    for (uint64_t l = 0; l < nl; ++l) {
+        uint64_t nb;
+        if (fread(&terms[l], 8, 1, in) != 1 || fread(&nb, 8, 1, in) != 1) return 1;
+        bounds[l].resize(nb);
+        if (nb && fread(bounds[l].data(), 8, nb, in) != nb) return 1;
+        calls += nb;
+    }
+    fclose(in);
+    double best = 1e300;
+    uint64_t checksum = 0;
+    for (size_t pass = 0; pass < passes; ++pass) {
+        std::vector<uint64_t> acc(n_threads, 0);
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> threads;
+        for (size_t t = 0; t < n_threads; ++t) {
+            threads.emplace_back([&, t]() {
+                uint64_t a = 0;
+                for (size_t l = t; l < nl; l += n_threads) {
+                    auto e = index[terms[l]];
+                    for (uint64_t b : bounds[l]) { e.next_geq(b); a += e.docid(); if (e.docid() < index.num_docs()) a += e.freq(); }
+                }
+                acc[t] = a;
+            });
+        }
+        for (auto& th : threads) th.join();
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        checksum = 0;
+        for (auto a : acc) checksum += a;
+    }
+    printf("{\"type\": \"%s\", \"lists\": %llu, \"threads\": %zu, \"calls\": %llu, \"seconds\": %.6f, \"calls_per_s\": %.1f, \"checksum\": %llu}\n",
+           argv[2], (unsigned long long)nl, n_threads, (unsigned long long)calls, best, calls / best, (unsigned long long)checksum);
+    return 0;
+}
+
 template <typename Index>
 int cmd_info(int, char** argv)
 {
@@ -385,6 +488,8 @@ int dispatch(std::string const& cmd, int argc, char** argv)
     if (cmd == "nextgeq") return cmd_nextgeq<Index>(argc, argv);
     if (cmd == "bench") return cmd_bench<Index>(argc, argv);
     if (cmd == "info") return cmd_info<Index>(argc, argv);
+    if (cmd == "scan") return cmd_scan<Index>(argc, argv);
+    if (cmd == "geqbench") return cmd_geqbench<Index>(argc, argv);
     std::cerr << "unknown command " << cmd << std::endl;
     return 1;
 }

@@ -26,6 +26,7 @@ DATA = os.path.join(BIN, "data")
 GOLDEN = os.path.join(REPO, "tests", "golden")
 TYPES_FULL = ["block_optpfor", "block_interpolative", "block_varint", "block_qmx", "opt", "uniform", "single", "ef", "block_mixed"]
 OPS = "and:or:ranked_and:wand:maxscore:ranked_or"
+FREQ_OPS = "and_freq:or_freq"          # and_query<true> / or_query<true> (queries.hpp:73-76,116-118): separate dump, added in round 2
 
 
 def run(*cmd, **kw):
@@ -77,6 +78,7 @@ def build_all(prefix, out_prefix, types, queries_path):
     for flavour, tool in (("stock", "ref_tool"), ("strict", "ref_tool_strict")):
         run(os.path.join(BIN, tool), "dump", types[0], out_prefix + "." + types[0] + ".idx", out_prefix + ".wand",
             queries_path, out_prefix + ".expected." + flavour + ".bin", OPS)
+    dump_freq_ops(out_prefix, types, queries_path)
     # every index type holds the same postings, so the reference returns the same bytes for each of them
     want = open(out_prefix + ".expected.strict.bin", "rb").read()
     for t in types[1:]:
@@ -88,7 +90,25 @@ def build_all(prefix, out_prefix, types, queries_path):
             raise RuntimeError("reference results differ between %s and %s" % (types[0], t))
 
 
+def dump_freq_ops(out_prefix, types, queries_path):
+    """and_freq / or_freq results of the reference (the operators also touch freq() of every match; the return value is the
+    match count) from the first index type, cross-checked on one Elias-Fano type."""
+    out = out_prefix + ".expected.freqops.bin"
+    run(os.path.join(BIN, "ref_tool_strict"), "dump", types[0], out_prefix + "." + types[0] + ".idx", out_prefix + ".wand", queries_path, out, FREQ_OPS)
+    if "opt" in types:
+        tmp = out_prefix + ".check.freqops.bin"
+        run(os.path.join(BIN, "ref_tool_strict"), "dump", "opt", out_prefix + ".opt.idx", out_prefix + ".wand", queries_path, tmp, FREQ_OPS)
+        same = open(tmp, "rb").read() == open(out, "rb").read()
+        os.remove(tmp)
+        if not same:
+            raise RuntimeError("reference and_freq / or_freq results differ between %s and opt" % types[0])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "freqops":      # only the round-2 addition, from the indexes already built
+        dump_freq_ops(os.path.join(DATA, "T"), TYPES_FULL, os.path.join(DATA, "T.queries"))
+        dump_freq_ops(os.path.join(GOLDEN, "mini"), TYPES_FULL, os.path.join(GOLDEN, "mini.queries"))
+        return
     os.makedirs(DATA, exist_ok=True)
     os.makedirs(GOLDEN, exist_ok=True)
     tcoll = os.path.join(REF, "test", "test_data", "test_collection")
