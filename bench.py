@@ -183,14 +183,17 @@ def cpu_baseline_for(paths, op, nq, itype="block_optpfor", single_prefix=1000):
     return base
 
 
-def parity_block(d, paths, op, k, nq, counts, scores, itype="block_optpfor"):
-    """Every query of the step against the reference's own results for the same index file."""
+def parity_block(d, paths, op, k, qidx, counts, scores, itype="block_optpfor"):
+    """Every query of the step against the reference's own results for the same index file.  qidx[j] = position in the
+    query file of the j-th query of the step (the step runs the queries in the scheduler's cost-balanced order)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from util import load_dump
     tmp = os.path.join(os.path.dirname(paths["index"]), "check.%s.%s.bin" % (itype, op))
-    ref_tool("dump", itype, paths[itype], paths["wand"], paths["queries"], tmp, op, k, nq, strict=True)
+    nq = len(qidx)
+    ref_tool("dump", itype, paths[itype], paths["wand"], paths["queries"], tmp, op, k, int(max(qidx)) + 1 if nq else 0, strict=True)
     ec, es = load_dump(tmp, (op,))[op]
+    ec, es = ec[qidx], es[qidx]
     out = {"queries_checked": int(nq), "counts_bit_exact": bool(np.array_equal(ec, counts[:nq])), "against": "ds2i reference, -ffp-contract=off build, same index file"}
     if op in d.RANKED:
         out["scores_bit_exact"] = bool(np.array_equal(es.view(np.uint32), scores[:nq].view(np.uint32)))
@@ -348,7 +351,7 @@ def main():
         """This rank's cost-balanced share of the first `total` queries of the file (+ the shard sizes of all ranks)."""
         allq = d.read_queries(paths["queries"], total)
         shards = balanced_shards(query_costs(index, allq), world)
-        return [allq[i] for i in shards[rank]], [len(s) for s in shards]
+        return [allq[i] for i in shards[rank]], [len(s) for s in shards], np.asarray(shards[rank])
 
     log("[bench] rank %d: index in HBM (%.1f MB) in %.1f s" % (rank, index.device_bytes() / 1e6, time.time() - t0))
 
@@ -432,7 +435,7 @@ def main():
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg, "kernel_ms": kern, "counters": st}
 
     total_q = args.queries * world if args.scaling == "weak" else args.queries
-    queries, shard_sizes = shard_for(total_q)
+    queries, shard_sizes, qidx = shard_for(total_q)
     m = measure(args.op, queries, shard_sizes)
     also_m = {}
     if args.op == "ranked_and" and not args.no_also:
@@ -440,7 +443,7 @@ def main():
             also_m[op2] = measure(op2, queries, shard_sizes)            # the second half of BASELINE.json's metric, same protocol
     strong_m = None
     if world > 1 and args.scaling == "weak" and not args.no_also:
-        sq, ssz = shard_for(args.queries)                               # strong scaling: the 10k-query batch of N = 1 cut over the ranks
+        sq, ssz, _ = shard_for(args.queries)                               # strong scaling: the 10k-query batch of N = 1 cut over the ranks
         strong_m = {op2: measure(op2, sq, ssz) for op2 in ((args.op, "wand") if args.op == "ranked_and" else (args.op,))}
 
     if rank != 0:
@@ -482,10 +485,10 @@ def main():
         nq = len(queries)
         try:
             line["cpu_baseline"] = cpu_baseline_for(paths, args.op, nq)
-            line["parity"] = parity_block(d, paths, args.op, args.k, nq, m["counts"], m["scores"])
+            line["parity"] = parity_block(d, paths, args.op, args.k, qidx, m["counts"], m["scores"])
             for op2, m2 in also_m.items():
                 line["also"][op2]["cpu_baseline"] = cpu_baseline_for(paths, op2, nq)
-                line["also"][op2]["parity"] = parity_block(d, paths, op2, args.k, nq, m2["counts"], m2["scores"])
+                line["also"][op2]["parity"] = parity_block(d, paths, op2, args.k, qidx, m2["counts"], m2["scores"])
             # the same roofline with the bytes the REFERENCE algorithm decodes (its own block_profiler) instead of the
             # device counters: what SURVEY.md 8d defines as algorithmic bytes
             for op2, tgt in [(args.op, line)] + [(o, line["also"][o]) for o in also_m]:
@@ -511,7 +514,7 @@ def main():
         if have_opt:
             try:
                 from ds2i_b200 import bench_opt
-                line["also"].update(bench_opt.legs(d, args, paths, queries, wdata, peak, measure, line_of, cpu_baseline_for, parity_block, ref_tool))
+                line["also"].update(bench_opt.legs(d, args, paths, queries, qidx, wdata, peak, measure, line_of, cpu_baseline_for, parity_block, ref_tool))
             except Exception as e:
                 line["also"]["pef"] = {"failed": repr(e)}
     print(json.dumps(line), flush=True)

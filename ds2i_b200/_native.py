@@ -16,7 +16,7 @@ SYMBOLS = [
     "ds2i_gpu_query_batch", "ds2i_gpu_query_batch_docids", "ds2i_gpu_batch_prepare", "ds2i_gpu_batch_run", "ds2i_gpu_batch_run_ex", "ds2i_gpu_batch_fetch", "ds2i_gpu_batch_fetch_docids",
     "ds2i_gpu_batch_stats", "ds2i_gpu_batch_device_results", "ds2i_gpu_batch_device_docids", "ds2i_gpu_merge_shards", "ds2i_gpu_batch_free",
     "ds2i_gpu_decode_lists", "ds2i_gpu_next_geq_batch",
-    "ds2i_gpu_decode_lists_checksum", "ds2i_gpu_index_type_known", "ds2i_gpu_batch_wait", "ds2i_gpu_batch_device_fused",
+    "ds2i_gpu_decode_lists_checksum", "ds2i_gpu_index_list_bytes", "ds2i_gpu_index_type_known", "ds2i_gpu_batch_wait", "ds2i_gpu_batch_device_fused",
     "ds2i_gpu_group_open", "ds2i_gpu_group_close", "ds2i_gpu_group_size", "ds2i_gpu_group_index", "ds2i_gpu_group_query_batch",
 ]
 
@@ -48,6 +48,7 @@ def lib():
         f.restype = C.c_uint64
     L.ds2i_gpu_index_set_global_stats.argtypes = [vp, u64p, C.c_size_t, C.c_uint64]
     L.ds2i_gpu_index_list_sizes.argtypes = [vp, u32p, C.c_size_t, u64p]
+    L.ds2i_gpu_index_list_bytes.argtypes = [vp, u32p, C.c_size_t, u64p]
     L.ds2i_gpu_wand_open.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.ds2i_gpu_wand_open_file.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.ds2i_gpu_wand_close.argtypes = [vp]

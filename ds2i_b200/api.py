@@ -85,6 +85,13 @@ class Index:
         _native.check(_native.lib().ds2i_gpu_index_list_sizes(self._h, _p(terms, C.c_uint32), len(terms), _p(out, C.c_uint64)))
         return out
 
+    def list_bytes(self, terms):
+        """Compressed bytes of each list in the index file (ds2i_gpu_index_list_bytes)."""
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        out = np.zeros(len(terms), dtype=np.uint64)
+        _native.check(_native.lib().ds2i_gpu_index_list_bytes(self._h, _p(terms, C.c_uint32), len(terms), _p(out, C.c_uint64)))
+        return out
+
     def decode_lists(self, terms):
         """docid()/freq() of every posting of index[term], as next() delivers them.
         Returns (offsets, docs, freqs, elapsed_ms)."""

@@ -15,9 +15,9 @@
 //   wand_data ctor / map                wand_data.hpp:16-52,71-78
 //
 //   ds2i_build gen   <prefix> <num_docs> <num_terms> <seed> [scale=0.35] [nqueries=10000] [qseed]
-//   ds2i_build index <block_optpfor|block_interpolative> <collection prefix> <out.idx> [threads]
+//   ds2i_build index <block_optpfor|block_interpolative|opt> <collection prefix> <out.idx> [threads]
 //   ds2i_build wand  <collection prefix> <out.wand> [threads]
-//   ds2i_build synth <out prefix> <num_docs> <num_terms> <seed> [threads] [nqueries] [types=block_optpfor]
+//   ds2i_build synth <out prefix> <num_docs> <num_terms> <seed> [threads] [nqueries] [types=block_optpfor, ':'-separated]
 //        -> <out>.block_optpfor.idx, <out>.wand, <out>.queries without materialising the collection
 //   ds2i_build shard <block_optpfor|block_interpolative> <collection prefix> <out prefix> <G> [threads]
 //        document-partitioned shards: shard g holds the documents [g*N/G, (g+1)*N/G) with local
@@ -518,6 +518,248 @@ static void build_block_index(list_source const& src, codec_id codec, std::strin
     fclose(f);
 }
 
+// ------------------------------------------------------------------------------------------------
+// `opt` index: freq_index<partitioned_sequence<indexed_sequence>, positive_sequence<partitioned_sequence<strict_sequence>>>
+// (index_types.hpp:24-27).  The file must be byte-identical to create_freq_index's, so the SAME decisions have to be
+// taken: the (1 + eps) shortest-path partitioner over the same cost function with the same integer / double arithmetic
+// (optimal_partition.hpp:69-121, configuration.hpp:29-31: eps1 = 0.03, eps2 = 0.3, fix cost 64 bits), the cheapest of
+// Elias-Fano / ranked bitvector / all-ones per partition (indexed_sequence.hpp:24-84, strict_sequence.hpp:32-98), and
+// the bit layouts of Appendix B.6 of SURVEY.md (compact_elias_fano.hpp:14-135, compact_ranked_bitvector.hpp:14-115,
+// partitioned_sequence.hpp:22-120, positive_sequence.hpp:14-30, freq_index.hpp:64-96, bitvector_collection.hpp:22-41).
+// Restated from those specifications; tests/test_builder.py compares the result with the reference-built fixtures.
+struct bit_sink : bitvec_builder {
+    void push(uint64_t bits, uint32_t len) {                         // append_bits
+        if (!len) return;
+        uint64_t at = size;
+        zero_extend(len);
+        set_bits(at, bits, len);
+    }
+    void push_all(bitvec_builder const& o) {                          // append(bit_vector_builder)
+        if (!o.size) return;
+        const uint64_t at = size, shift = at & 63;
+        zero_extend(o.size);
+        uint64_t wi = at >> 6;
+        const size_t nw = size_t((o.size + 63) / 64);
+        if (!shift) { std::copy(o.w.begin(), o.w.begin() + nw, w.begin() + wi); return; }
+        for (size_t i = 0; i < nw; ++i) {
+            w[wi + i] |= o.w[i] << shift;
+            if (wi + i + 1 < w.size()) w[wi + i + 1] |= o.w[i] >> (64 - shift);
+        }
+    }
+    void gamma(uint64_t v) {                                           // write_gamma (integer_codes.hpp:6-13)
+        uint64_t nn = v + 1, l = msb64(nn), hb = uint64_t(1) << l;
+        push(hb, uint32_t(l + 1));
+        push(nn ^ hb, uint32_t(l));
+    }
+    void delta(uint64_t v) {                                           // write_delta (:32-39)
+        uint64_t nn = v + 1, l = msb64(nn), hb = uint64_t(1) << l;
+        gamma(l);
+        push(nn ^ hb, uint32_t(l));
+    }
+};
+
+struct ef_params { uint32_t log_s0 = 9, log_s1 = 8, log_rank1 = 9, log_rb_s1 = 8; };    // global_parameters.hpp:6-12
+static ef_params strict_params() { ef_params p; p.log_s0 = 63; p.log_rank1 = 63; return p; }   // strict_sequence.hpp:24-30
+
+static inline uint64_t ef_bits(uint64_t universe, uint64_t n, ef_params const& p) {      // compact_elias_fano::offsets::end
+    const uint64_t lower = universe > n ? msb64(universe / n) : 0;
+    const uint64_t hlen = n + (universe >> lower) + 2;
+    const uint64_t psize = ceil_log2(hlen);
+    return ((hlen - n) >> p.log_s0) * psize + (n >> p.log_s1) * psize + hlen + n * lower;
+}
+static inline uint64_t rb_bits(uint64_t universe, uint64_t n, ef_params const& p) {      // compact_ranked_bitvector::offsets::end
+    return (universe >> p.log_rank1) * ceil_log2(n + 1) + (n >> p.log_rb_s1) * ceil_log2(universe) + universe;
+}
+
+// compact_ranked_bitvector::write: rank samples every 2^log_rank1 positions, a select pointer every 2^log_rb_s1 ones, the bitmap
+static void rb_write(bit_sink& out, const uint64_t* v, uint64_t universe, uint64_t n, ef_params const& p) {
+    const uint64_t base = out.size, rsize = ceil_log2(n + 1), psize = ceil_log2(universe);
+    const uint64_t nsamples = universe >> p.log_rank1, nptrs = n >> p.log_rb_s1;
+    const uint64_t ptr_off = base + nsamples * rsize, bits_off = ptr_off + nptrs * psize;
+    out.zero_extend(bits_off + universe - base);
+    // sample k (k >= 1) = number of ones before position k << log_rank1
+    auto samples_between = [&](uint64_t from, uint64_t to, uint64_t rank) {
+        const uint64_t step = uint64_t(1) << p.log_rank1;
+        for (uint64_t k = (from + step - 1) / step; (k << p.log_rank1) < to; ++k)
+            if (k) out.set_bits(base + (k - 1) * rsize, rank, uint32_t(rsize));
+    };
+    const uint64_t smask = (uint64_t(1) << p.log_rb_s1) - 1;
+    uint64_t prev = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t x = v[i];
+        if (i && x <= prev) throw std::runtime_error("sequence is not strictly increasing");
+        out.set(bits_off + x);
+        if (i && !(i & smask)) out.set_bits(ptr_off + ((i >> p.log_rb_s1) - 1) * psize, x, uint32_t(psize));
+        samples_between(prev + 1, x + 1, i);
+        prev = x;
+    }
+    samples_between(prev + 1, universe, n);
+}
+
+// cost in bits of the cheapest representation of n values in [0, universe) (indexed_sequence / strict_sequence ::bitsize)
+static inline uint64_t partition_bits(uint64_t universe, uint64_t n, bool strict, ef_params const& p, int* type = nullptr) {
+    uint64_t best = universe == n ? 0 : ~uint64_t(0);
+    int t = 2;                                                       // all_ones
+    if (best) {
+        const uint64_t ef = (strict ? ef_bits(universe - n + 1, n, p) : ef_bits(universe, n, p)) + 1;
+        if (ef < best) { best = ef; t = 0; }
+        const uint64_t rb = rb_bits(universe, n, p) + 1;
+        if (rb < best) { best = rb; t = 1; }
+    }
+    if (type) *type = t;
+    return best;
+}
+
+static void partition_write(bit_sink& out, const uint64_t* v, uint64_t universe, uint64_t n, bool strict, std::vector<uint64_t>& tmp) {
+    const ef_params p = strict ? strict_params() : ef_params();
+    int type;
+    partition_bits(universe, n, strict, p, &type);
+    if (type != 2) out.push(uint64_t(type), 1);                     // the type bit is absent for all-ones partitions
+    if (type == 0) {
+        if (!strict) { ef_write(out, v, universe, n, p.log_s0, p.log_s1); return; }
+        tmp.resize(n);                                               // strict_elias_fano: v_i - i in a universe smaller by n - 1
+        for (uint64_t i = 0; i < n; ++i) tmp[i] = v[i] - i;
+        ef_write(out, tmp.data(), universe - n + 1, n, p.log_s0, p.log_s1);
+    } else if (type == 1) {
+        rb_write(out, v, universe, n, p);
+    }
+}
+
+// End positions of the partitions chosen by the reference's approximate shortest-path search.  One window per cost
+// bound lb, lb (1 + eps2), lb (1 + eps2)^2, ... < lb / eps1; every window slides over the sequence keeping its cost
+// just above its bound; an edge (i -> window end) relaxes the path cost.  Types follow the reference exactly (32-bit
+// element arithmetic for the window universe, the bound truncated to an integer after every multiplication).
+static std::vector<uint32_t> choose_partitions(const uint64_t* v, uint64_t universe, uint64_t n, bool strict) {
+    const ef_params p = strict ? strict_params() : ef_params();
+    const double eps1 = 0.03, eps2 = 0.3;
+    const uint64_t fix_cost = 64;
+    auto cost = [&](uint64_t u, uint64_t m) { return partition_bits(u, m, strict, p) + fix_cost; };
+    struct window { uint32_t start = 0, end = 0, lo = 0, hi = 0; uint64_t bound = 0; };
+    const uint64_t whole = cost(universe, n);
+    std::vector<uint64_t> best(n + 1, whole);
+    best[0] = 0;
+    std::vector<window> wins;
+    const uint64_t lb = cost(1, 1);
+    for (uint64_t bound = lb; double(bound) < double(lb) / eps1;) {
+        window w; w.lo = uint32_t(v[0]); w.bound = bound;
+        wins.push_back(w);
+        if (bound >= whole) break;
+        bound = uint64_t(double(bound) * (1 + eps2));
+    }
+    std::vector<uint32_t> from(n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t reach = uint64_t(i) + 1;
+        for (window& w : wins) {
+            while (w.end < reach) { w.hi = uint32_t(v[w.end]); ++w.end; }
+            while (true) {
+                const uint64_t c = cost(uint64_t(uint32_t(w.hi - w.lo + 1)), uint64_t(w.end - w.start));
+                if (best[i] + c < best[w.end]) { best[w.end] = best[i] + c; from[w.end] = i; }
+                reach = w.end;
+                if (w.end == n || c >= w.bound) break;
+                w.hi = uint32_t(v[w.end]); ++w.end;
+            }
+            w.lo = uint32_t(v[w.start]) + 1; ++w.start;
+        }
+    }
+    std::vector<uint32_t> ends;
+    for (uint32_t at = uint32_t(n); at; at = from[at]) ends.push_back(at);
+    std::reverse(ends.begin(), ends.end());
+    return ends;
+}
+
+// partitioned_sequence::write (partitioned_sequence.hpp:22-120)
+static void partitioned_write(bit_sink& out, const uint64_t* v, uint64_t universe, uint64_t n, bool strict) {
+    const std::vector<uint32_t> ends = choose_partitions(v, universe, n, strict);
+    const uint64_t parts = ends.size();
+    out.gamma(parts - 1);                                            // write_gamma_nonzero
+    std::vector<uint64_t> rel, tmp;
+    if (parts == 1) {
+        const uint64_t base = v[0];
+        rel.resize(n);
+        for (uint64_t i = 0; i < n; ++i) rel[i] = v[i] - base;
+        out.push(base, uint32_t(ceil_log2(universe)));
+        if (n > 1) out.delta(base + rel.back() + 1 == universe ? 0 : rel.back());      // 0 = "tight": the universe ends with the last value
+        partition_write(out, rel.data(), rel.back() + 1, n, strict, tmp);
+        return;
+    }
+    bit_sink bodies;
+    std::vector<uint64_t> body_ends, uppers{v[0]}, sizes(ends.begin(), ends.end());
+    uint64_t base = v[0], at = 0;
+    for (uint64_t pi = 0; pi < parts; ++pi) {
+        rel.clear();
+        for (; at < ends[pi]; ++at) rel.push_back(v[at] - base);
+        partition_write(bodies, rel.data(), rel.back() + 1, rel.size(), strict, tmp);
+        body_ends.push_back(bodies.size);
+        uppers.push_back(v[at - 1]);
+        base = v[at - 1] + 1;
+    }
+    const ef_params g;                                               // the two directories use the index-wide parameters
+    bit_sink bsizes, buppers;
+    ef_write(bsizes, sizes.data(), n, parts - 1, g.log_s0, g.log_s1);
+    ef_write(buppers, uppers.data(), universe, parts + 1, g.log_s0, g.log_s1);
+    const uint64_t ebits = ceil_log2(bodies.size + 1);
+    out.gamma(ebits);
+    out.push_all(bsizes);
+    out.push_all(buppers);
+    for (uint64_t pi = 0; pi + 1 < parts; ++pi) out.push(body_ends[pi], uint32_t(ebits));
+    out.push_all(bodies);
+}
+
+struct built_bits { bit_sink docs, freqs; std::vector<uint64_t> docs_len, freqs_len; };
+
+static void write_bit_collection(FILE* f, std::vector<built_bits> const& slots, bool freqs, uint64_t num_lists) {
+    bit_sink all;
+    std::vector<uint64_t> starts;
+    starts.reserve(num_lists);
+    uint64_t total = 0;
+    for (auto const& s : slots) for (uint64_t l : (freqs ? s.freqs_len : s.docs_len)) { starts.push_back(total); total += l; }
+    if (starts.size() != num_lists) throw std::runtime_error("internal: list count mismatch");
+    all.w.reserve(size_t(total / 64 + 2));
+    for (auto const& s : slots) all.push_all(freqs ? s.freqs : s.docs);
+    bit_sink ends;
+    ef_write(ends, starts.data(), total, num_lists, 9, 8);
+    put_u64(f, num_lists);
+    put_u64(f, ends.size); put_u64(f, ends.w.size()); fwrite(ends.w.data(), 8, ends.w.size(), f);
+    put_u64(f, all.size); put_u64(f, all.w.size()); fwrite(all.w.data(), 8, all.w.size(), f);
+}
+
+// freq_index file: flags | 5 params | m_num_docs | docs collection | freqs collection (freq_index.hpp:234-243)
+static void build_opt_index(list_source const& src, std::string const& out_path, unsigned threads,
+                            std::vector<std::atomic<uint32_t>>* doclen) {
+    std::vector<built_bits> slots(std::max<size_t>(1, std::min<size_t>(src.num_lists, size_t(threads) * 16)) + 2);
+    parallel_ranges(src.est_len, threads, [&](size_t c, uint64_t lo, uint64_t hi) {
+        std::vector<uint32_t> docs, freqs;
+        std::vector<uint64_t> dv, fv;
+        built_bits& bb = slots[c];
+        for (uint64_t i = lo; i < hi; ++i) {
+            src.get(i, docs, freqs);
+            const uint64_t n = docs.size();
+            if (!n) throw std::invalid_argument("List must be nonempty");
+            dv.assign(docs.begin(), docs.end());
+            fv.resize(n);
+            uint64_t occ = 0;
+            for (uint64_t k = 0; k < n; ++k) { occ += freqs[k]; fv[k] = occ; }       // positive_sequence: prefix sums, strictly increasing
+            const uint64_t d0 = bb.docs.size, f0 = bb.freqs.size;
+            bb.docs.gamma(occ - 1);                                                   // list header (freq_index.hpp:66-71)
+            if (occ > 1) bb.docs.push(n, uint32_t(ceil_log2(occ + 1)));
+            partitioned_write(bb.docs, dv.data(), src.num_docs, n, false);
+            partitioned_write(bb.freqs, fv.data(), occ + 1, n, true);
+            bb.docs_len.push_back(bb.docs.size - d0);
+            bb.freqs_len.push_back(bb.freqs.size - f0);
+            if (doclen) for (size_t k = 0; k < n; ++k) (*doclen)[docs[k]].fetch_add(freqs[k], std::memory_order_relaxed);
+        }
+    });
+    FILE* f = fopen(out_path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + out_path);
+    put_u64(f, 0);
+    const uint8_t params[5] = {9, 8, 9, 8, 7};
+    fwrite(params, 1, 5, f);
+    put_u64(f, src.num_docs);
+    write_bit_collection(f, slots, false, src.num_lists);
+    write_bit_collection(f, slots, true, src.num_lists);
+    fclose(f);
+}
+
 // bm25::doc_term_weight (bm25.hpp:11-15) — same expression, same compiler flags as the reference tool
 static inline float doc_term_weight(uint64_t freq, float norm_len) {
     const float b = 0.5f, k1 = 1.2f;
@@ -582,7 +824,8 @@ int main(int argc, char** argv) {
             std::shared_ptr<mapped> dm, fm;
             list_source src = collection_source(argv[3], dm, fm);
             unsigned threads = argc > 5 ? unsigned(atoi(argv[5])) : hw;
-            build_block_index(src, parse_codec(argv[2]), argv[4], threads, nullptr);
+            if (std::string(argv[2]) == "opt") build_opt_index(src, argv[4], threads, nullptr);
+            else build_block_index(src, parse_codec(argv[2]), argv[4], threads, nullptr);
             return 0;
         }
         if (cmd == "wand" && argc >= 4) {
@@ -638,7 +881,8 @@ int main(int argc, char** argv) {
                 size_t end = types.find(':', start);
                 if (end == std::string::npos) end = types.size();
                 std::string t = types.substr(start, end - start);
-                build_block_index(src, parse_codec(t), prefix + "." + t + ".idx", threads, first ? &doclen : nullptr);
+                if (t == "opt") build_opt_index(src, prefix + ".opt.idx", threads, first ? &doclen : nullptr);
+                else build_block_index(src, parse_codec(t), prefix + "." + t + ".idx", threads, first ? &doclen : nullptr);
                 first = false;
                 start = end + 1;
             }
@@ -689,7 +933,7 @@ int main(int argc, char** argv) {
             }
             return 0;
         }
-        if (cmd == "types") { printf("block_optpfor block_interpolative\n"); return 0; }      // index types this builder writes
+        if (cmd == "types") { printf("block_optpfor block_interpolative opt\n"); return 0; }      // index types this builder writes
         fprintf(stderr, "usage: ds2i_build gen|index|wand|synth|shard|types ... (see the header of builder.cpp)\n");
         return 1;
     } catch (std::exception const& e) {

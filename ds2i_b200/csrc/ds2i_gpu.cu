@@ -179,6 +179,7 @@ struct ds2i_gpu_batch {
     uint32_t last_k = 0;
     bool last_ranked = false;
     bool pending = false;          // an asynchronous run has been launched and not waited for yet
+    size_t counters_bytes = 0;     // work counters + statistics: one contiguous stretch of the arena, zeroed before every run
     // ONE device allocation per batch: the uploaded descriptors first (one H2D copy), then the device-only buffers
     dev_buf<uint8_t> arena;
     dev_view<uint32_t> q_begin, term, sched, work_counter;
@@ -356,6 +357,20 @@ extern "C" int ds2i_gpu_index_list_sizes(const ds2i_gpu_index* ix, const uint32_
     for (size_t i = 0; i < nterms; ++i) {
         if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
         out_sizes[i] = list_size_of(ix, terms[i]);
+    }
+    return DS2I_OK;
+}
+
+extern "C" int ds2i_gpu_index_list_bytes(const ds2i_gpu_index* ix, const uint32_t* terms, size_t nterms, uint64_t* out_bytes) {
+    if (!ix || (!terms && nterms) || (!out_bytes && nterms)) return fail(DS2I_E_ARG, "null argument");
+    for (size_t i = 0; i < nterms; ++i) {
+        if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
+        if (ix->kind == KIND_PEF) out_bytes[i] = (ix->pef->host_dir[terms[i]].bits + 7) / 8;
+        else {
+            ListDir const& d = ix->host_dir[terms[i]];
+            const uint64_t blocks = (uint64_t(d.n) + BLOCK - 1) / BLOCK;
+            out_bytes[i] = 4 * blocks + 4 * (blocks - 1) + d.data_bytes;          // block_maxs + block_endpoints + block data
+        }
     }
     return DS2I_OK;
 }
@@ -669,7 +684,8 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     CUDA_TRY(b->arena.alloc(lay.bytes));
     uint8_t* d = b->arena.p;
     if (upload_bytes) CUDA_TRY(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, 0));
-    CUDA_TRY(cudaMemsetAsync(d + o_counter, 0, o_and_counts - o_counter, 0));          // work counters + stats
+    b->counters_bytes = o_and_counts - o_counter;
+    CUDA_TRY(cudaMemsetAsync(d + o_counter, 0, b->counters_bytes, 0));          // work counters + stats
     b->q_begin.p = reinterpret_cast<uint32_t*>(d + o_q_begin); b->term.p = reinterpret_cast<uint32_t*>(d + o_term);
     b->sched.p = reinterpret_cast<uint32_t*>(d + o_sched); b->q_weight.p = reinterpret_cast<float*>(d + o_qw);
     b->max_weight.p = reinterpret_cast<float*>(d + o_mw); b->ord_size.p = d + o_os; b->ord_maxw.p = d + o_om;
@@ -826,7 +842,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     db.max_weight = b->max_weight.p; db.ord_size = b->ord_size.p; db.ord_maxw = b->ord_maxw.p;
     db.sched = b->sched.p; db.work_counter = b->work_counter.p; db.out_counts = b->out_counts.p;
     db.out_scores = b->out_scores.p; db.out_docids = b->out_docids.p; db.stats = b->stats.p;
-    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, 16 + 16 * 8));          // work counters and, right behind them, the statistics
+    CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, b->counters_bytes));          // work counters and, behind them in the arena, the statistics
     CUDA_TRY(cudaEventRecord(b->ev0));
     int rc = DS2I_OK;
     if (b->nq) {

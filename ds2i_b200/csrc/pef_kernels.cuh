@@ -445,7 +445,7 @@ static inline void pef_parse_any(int variant, bitvec_view const& bv, uint64_t of
 
 struct PefIndexHost {
     uint64_t size = 0, num_docs = 0, device_bytes = 0;
-    struct host_list { uint64_t n; };
+    struct host_list { uint64_t n; uint64_t bits; };      // postings; bits of the list in the docs + freqs bit vectors
     std::vector<host_list> host_dir;
     PefSeqHost docs, freqs;
     PefIndexDev dev{};
@@ -489,6 +489,7 @@ struct PefIndexHost {
                 if (occurrences > 1) n = it.take(uint32_t(ceil_log2_u64(occurrences + 1)));
                 if (n == 0 || n > num_docs) throw format_error("bad list length");
                 host_dir[i].n = n;
+                host_dir[i].bits = ((i + 1 < size ? dstart[i + 1] : dbits.bits) - dstart[i]) + ((i + 1 < size ? fstart[i + 1] : fbits.bits) - fstart[i]);
                 docs.lists[i] = PefListDir{docs.parts.size(), 0u, uint32_t(n)};
                 pef_parse_any(variant, dbits, it.pos, num_docs, n, gp, docs.parts);
                 docs.lists[i].nparts = uint32_t(docs.parts.size() - docs.lists[i].first_part);

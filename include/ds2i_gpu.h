@@ -75,6 +75,10 @@ uint64_t ds2i_gpu_index_device_bytes(const ds2i_gpu_index*);
  * every score equals the one the reference computes on the unsharded collection.  df == NULL clears them. */
 int ds2i_gpu_index_set_global_stats(ds2i_gpu_index*, const uint64_t* df, size_t nterms, uint64_t num_docs_total);
 int ds2i_gpu_index_list_sizes(const ds2i_gpu_index*, const uint32_t* terms, size_t nterms, uint64_t* out_sizes);
+/* Compressed bytes of index[term] in the file: block_maxs + block_endpoints + block data for the block indexes
+ * (block_posting_list.hpp:14-53), the list's bits in the docs and freqs bit vectors for the Elias-Fano family
+ * (bitvector_collection.hpp:57-67) — the algorithmic bytes of a full scan of the list. */
+int ds2i_gpu_index_list_bytes(const ds2i_gpu_index*, const uint32_t* terms, size_t nterms, uint64_t* out_bytes);
 
 /* ---- wand_data: replaces succinct::mapper::map(wdata, md) (queries.cpp:90-95; wand_data.hpp:55-78). */
 int ds2i_gpu_wand_open(const void* file_bytes, size_t nbytes, int device, ds2i_gpu_wand** out);

@@ -38,7 +38,7 @@ def mini_collection(tmp_path_factory):
     return prefix
 
 
-@pytest.mark.parametrize("itype", ["block_optpfor", "block_interpolative"])
+@pytest.mark.parametrize("itype", ["block_optpfor", "block_interpolative", "opt"])
 @pytest.mark.parametrize("threads", [1, 5])
 def test_index_byte_identical_to_reference_build(builder, mini_collection, tmp_path, itype, threads):
     out = str(tmp_path / ("my.%s.idx" % itype))
