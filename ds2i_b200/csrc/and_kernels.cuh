@@ -71,12 +71,13 @@ __device__ __forceinline__ uint32_t warp_upper_group(const uint32_t* a, uint32_t
 
 // per query term: cursor + the decoded docids of the current block
 struct AndList {
-    uint64_t data_off;      // absolute byte offset of the list's block data inside m_lists
+    uint64_t data_off;      // absolute byte offset of the list's block data inside m_lists (Elias-Fano: first partition of the docs sequence)
     uint32_t bfirst;        // the list's first entry in the block directory
     uint32_t nblocks;
     uint32_t n;
     uint32_t last_max;      // last docid of the list
-    uint32_t pad0, pad1;
+    uint32_t term;          // the list (the Elias-Fano path looks its freqs sequence up by it)
+    uint32_t pad1;
     // written together by lane 0 after every block decode (one 16-B store)
     uint32_t cur_block;     // 0xffffffff: not positioned yet
     uint32_t cur_max;       // last docid of the current block
@@ -136,6 +137,25 @@ __device__ __forceinline__ uint32_t and_decode_values(uint32_t stage_off, uint32
     return decode_interpolative_prefix(stage_off, off, size, sum_of_values, out_off, stack_off);
 }
 
+// cursor of list `term` into its slot (lane-private call: one lane per query term)
+template <int CODEC>
+__device__ __forceinline__ void and_list_setup(DevIndex const& idx, AndList* s, uint32_t term) {
+    const ListDir d = idx.dir[term];
+    const uint32_t bfirst = idx.bfirst[term];
+    uint32_t nblocks;
+    if (CODEC == CODEC_PEF) {
+        nblocks = idx.bfirst[term + 1] - bfirst;                     // windows never straddle partitions: not ceil(n / 128)
+        s->data_off = idx.pdocs.lists[term].first_part;
+    } else {
+        nblocks = (d.n + BLOCK - 1) / BLOCK;
+        s->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
+    }
+    s->bfirst = bfirst; s->nblocks = nblocks; s->n = d.n; s->term = term;
+    s->last_max = __ldg(idx.bdir + bfirst + nblocks - 1).x;
+    s->cur_block = 0xffffffffu;     // not positioned yet
+    s->cur_max = 0; s->cur_end = 0; s->freqs_off = 0;
+}
+
 struct AndCtx {             // warp-uniform registers
     const uint8_t* lists;
     uint32_t* stage;
@@ -148,10 +168,113 @@ struct AndCtx {             // warp-uniform registers
     uint32_t c_docs_blocks, c_freqs_blocks, c_bytes_docs, c_bytes_freqs, c_maxs, c_scored;
 };
 
+// ---- Elias-Fano index family: a "block" is a 128-element window of one partition of the docs sequence --------------------
+// Window b of the list -> its partition (the directory's second word: index of the partition inside the list) and the
+// elements [128 w, 128 w + 128) of it.  A body of up to STAGE_BYTES is copied into the warp's staging window with one TMA
+// bulk copy and decoded from shared memory (both windows of a two-window partition reuse the copy); longer bodies (the
+// single-partition sequences of very regular lists) are read in place.
+template <class List>
+__device__ __forceinline__ void pef_window_docs(AndCtx& c, DevIndex const& idx, List* s, uint32_t slot, uint32_t b, uint32_t part_rel, uint32_t cur_max) {
+    const unsigned lane = lane_id();
+    const PefPart p = pef_load_part(idx.pdocs.parts, s->data_off + part_rel);
+    const uint32_t i0 = (b - p.first_block) * BLOCK;
+    const uint32_t cnt = min(BLOCK, p.size - i0);
+    const uint64_t byte0 = (p.bit_off >> 3) & ~uint64_t(15);
+    const uint64_t byte1 = (((p.bit_off + p.body_bits + 7) >> 3) + 15) & ~uint64_t(15);
+    if (p.body_bits && byte1 - byte0 <= STAGE_BYTES) {
+        if (!(c.win_slot == slot && c.win_delta == part_rel)) {
+            __syncwarp();   // every lane is done reading the previous window
+            if (lane == 0) {
+                mbar_expect_tx(c.bar, uint32_t(byte1 - byte0));
+                tma_load_1d(c.stage, reinterpret_cast<const uint8_t*>(idx.pdocs.bits) + byte0, uint32_t(byte1 - byte0), c.bar);
+            }
+            mbar_wait(c.bar, c.phase);
+            c.phase ^= 1u;
+            c.win_slot = slot; c.win_delta = part_rel;
+        }
+        const StagedBits sb{reinterpret_cast<const uint64_t*>(c.stage), byte0 >> 3, uint32_t((byte1 - byte0) >> 3)};
+        const PefBody body = pef_open_body(idx.pdocs, sb, p, false);
+        pef_decode_range(sb, p, body, i0, cnt, s->docs);
+        DS2I_STAT(c.c_bytes_docs += (cnt * (p.body_bits >> 3)) / p.size;)
+    } else {
+        const GlobalBits gb{idx.pdocs.bits};
+        const PefBody body = pef_open_body(idx.pdocs, gb, p, false);
+        pef_decode_range(gb, p, body, i0, cnt, s->docs);
+        DS2I_STAT(c.c_bytes_docs += p.body_bits ? uint32_t((uint64_t(cnt) * (p.body_bits >> 3)) / p.size) : cnt;)
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) { const uint32_t e = lane + 32u * j; if (e >= cnt) s->docs[e] = 0xffffffffu; }
+    // cur_end: the window's partition; freqs_off: list position of the window's first element
+    if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, part_rel, p.begin + i0);
+    __syncwarp();
+    DS2I_STAT(c.c_docs_blocks += 1;)
+}
+
+// freq() - 1 of the postings of the current window of `s` -> the 128-word buffer at out.  positive_sequence over the strict
+// prefix sums c[] (positive_sequence.hpp:48-66): freq(i) = c[i] - c[i-1].  The freqs sequence has its own partitions; a docs
+// window may straddle two of them, so the range is decoded partition by partition.
+template <class List>
+__device__ __forceinline__ void pef_window_freqs(AndCtx& c, DevIndex const& idx, const List* s, uint32_t* out) {
+    const unsigned lane = lane_id();
+    const uint32_t b = s->cur_block;
+    const uint32_t g0 = s->freqs_off;                                   // list position of the window's first element
+    const PefPart dp = pef_load_part(idx.pdocs.parts, s->data_off + s->cur_end);
+    const uint32_t cnt = min(BLOCK, dp.size - (b - dp.first_block) * BLOCK);
+    const PefListDir fl = idx.pfreqs.lists[s->term];
+    const GlobalBits gb{idx.pfreqs.bits};
+    // partition of the freqs sequence holding position g0: last partition with begin <= g0 (32 probes per step)
+    uint32_t lo = 0, hi = fl.nparts;
+    while (hi - lo > 1) {
+        const uint32_t span = hi - lo, step = (span + 31u) / 32u, pi = lo + lane * step;
+        const bool le = pi < hi && __ldg(reinterpret_cast<const uint32_t*>(idx.pfreqs.parts + fl.first_part + pi) + 2) <= g0;      // PefPart::begin
+        const unsigned m = __ballot_sync(FULL, le);
+        const uint32_t f = 31u - __clz(m);
+        lo = lo + f * step;
+        hi = min(hi, lo + step);
+    }
+    uint32_t fp = lo, g = g0, prev = 0;
+    bool have_prev = false;
+    while (g < g0 + cnt) {
+        const PefPart p = pef_load_part(idx.pfreqs.parts, fl.first_part + fp);
+        const PefBody body = pef_open_body(idx.pfreqs, gb, p, true);
+        const uint32_t local = g - p.begin;
+        const uint32_t take = min(g0 + cnt - g, p.size - local);
+        if (!have_prev) {
+            // c[g0 - 1]: the value before a partition's first element is the previous partition's last value = base - 1
+            // (partition 0: the sum before the first element is 0); otherwise one more element is decoded
+            if (local == 0) prev = fp ? p.base - 1u : 0u;
+            else {
+                pef_decode_range(gb, p, body, local - 1u, 1u, out);
+                prev = out[0];
+                __syncwarp();
+            }
+            have_prev = true;
+        }
+        pef_decode_range(gb, p, body, local, take, out + (g - g0));
+        g += take; ++fp;
+    }
+    // prefix sums -> freq - 1, in place
+    uint32_t v[5];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) { const uint32_t e = 4u * lane + j; v[j + 1] = e < cnt ? out[e] : 0u; }
+    v[0] = lane ? out[4u * lane - 1u] : prev;
+    __syncwarp();
+    uint4 r;
+    r.x = v[1] - v[0] - 1u; r.y = v[2] - v[1] - 1u; r.z = v[3] - v[2] - 1u; r.w = v[4] - v[3] - 1u;
+    reinterpret_cast<uint4*>(out)[lane] = r;
+    __syncwarp();
+    DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += cnt;)
+}
+
 // block_posting_list.hpp:292-319 with the block's metadata in hand: [e0, e1) = byte range of the block
 // pair inside the list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
 template <int CODEC, class List>
-__device__ __forceinline__ void and_decode_docs(AndCtx& c, List* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
+__device__ __forceinline__ void and_decode_docs(AndCtx& c, DevIndex const& idx, List* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
+    if constexpr (CODEC == CODEC_PEF) {
+        (void)e0; (void)prev_max;
+        pef_window_docs(c, idx, s, slot, b, e1, cur_max);
+        return;
+    }
     const unsigned lane = lane_id();
     const uint32_t n = s->n;
     const uint32_t cur_base = prev_max + 1u;
@@ -184,7 +307,12 @@ __device__ __forceinline__ void and_decode_docs(AndCtx& c, List* s, uint32_t slo
 // block pair is still staged; a block carried over from an earlier candidate batch is staged again.
 // Returns whether the buffer holds prefix sums (interpolative) instead of plain values.
 template <int CODEC, class List>
-__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, const List* s, uint32_t slot, uint32_t out_off) {
+__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, DevIndex const& idx, const List* s, uint32_t slot, uint32_t out_off) {
+    if constexpr (CODEC == CODEC_PEF) {
+        (void)slot;
+        pef_window_freqs(c, idx, s, smem_words(out_off));
+        return false;
+    }
     const uint32_t n = s->n, b = s->cur_block;
     const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
     const uint32_t freqs_off = s->freqs_off;
@@ -301,16 +429,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         if (lane < nt) {
             const uint32_t src = batch.ord_size[t0 + lane];
             if (RANKED) ws->qw[lane] = batch.q_weight[t0 + src];
-            const uint32_t term = batch.term[t0 + src];
-            const ListDir d = idx.dir[term];
-            const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-            const uint32_t bfirst = idx.bfirst[term];
-            AndList* s = &st[lane];
-            s->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
-            s->bfirst = bfirst; s->nblocks = nblocks; s->n = d.n;
-            s->last_max = __ldg(idx.bdir + bfirst + nblocks - 1).x;
-            s->cur_block = 0xffffffffu;     // not positioned yet
-            s->cur_max = 0; s->cur_end = 0; s->freqs_off = 0;
+            and_list_setup<CODEC>(idx, &st[lane], batch.term[t0 + src]);
         }
         __syncwarp();
 
@@ -333,7 +452,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             {
                 const uint32_t l = b0 - first_block;
                 const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
-                and_decode_docs<CODEC>(c, &st[0], 0u, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
+                and_decode_docs<CODEC>(c, idx, &st[0], 0u, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
                                        __shfl_sync(FULL, m_max, l));
             }
             const uint4 cv = reinterpret_cast<const uint4*>(st[0].docs)[lane];
@@ -348,7 +467,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             uint32_t f0_bytes = 0;
             if (RANKED) {
                 const uint32_t before = c.c_bytes_freqs;
-                const bool prefix = and_decode_freqs<CODEC>(c, &st[0], 0u, c.ftmp_off);
+                const bool prefix = and_decode_freqs<CODEC>(c, idx, &st[0], 0u, c.ftmp_off);
                 f0_bytes = c.c_bytes_freqs - before;
                 const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
                 f0[0] = fv.x; f0[1] = fv.y; f0[2] = fv.z; f0[3] = fv.w;
@@ -386,7 +505,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                         const bool fresh = cur_block == 0xffffffffu;
                         const BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
                                                             fresh ? 0u : s->cur_end, cmin);
-                        and_decode_docs<CODEC>(c, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+                        and_decode_docs<CODEC>(c, idx, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
                     }
                     const uint32_t cur_max = s->cur_max;
                     const uint32_t* d = s->docs;
@@ -430,7 +549,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                             for (int j = 0; j < 4; ++j)
                                 if (hitmask & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
                         }
-                        const bool prefix = and_decode_freqs<CODEC>(c, s, i, c.ftmp_off);
+                        const bool prefix = and_decode_freqs<CODEC>(c, idx, s, i, c.ftmp_off);
                         const float qw0 = ws->qw[0];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)

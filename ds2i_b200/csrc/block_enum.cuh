@@ -5,6 +5,7 @@
 // next_geq inside a block is a 128-wide compare + one warp reduction.
 #pragma once
 #include "codecs.cuh"
+#include "pef.cuh"
 
 namespace ds2i_gpu {
 
@@ -33,6 +34,10 @@ struct DevIndex {
     uint64_t num_lists;
     uint32_t num_docs;
     int codec;              // CODEC_*
+    // Elias-Fano index family (codec == CODEC_PEF): the two bit-vector collections; bdir / bfirst then hold the window
+    // directory of the docs sequences (last docid of every 128-element window, index of its partition inside the list;
+    // bfirst has num_lists + 1 entries) and dir[] only carries n
+    PefSeq pdocs, pfreqs;
 };
 
 struct ListState {

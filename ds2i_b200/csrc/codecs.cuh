@@ -10,7 +10,8 @@
 namespace ds2i_gpu {
 
 enum : int { CODEC_OPTPFOR = 0, CODEC_VARINT = 1, CODEC_INTERPOLATIVE = 2, CODEC_QMX = 3,
-             CODEC_MIXED = 4 /* mixed_block.hpp: one type byte in front of every full block */, CODEC_ANY = 99 /* decided at run time from the index */ };
+             CODEC_MIXED = 4 /* mixed_block.hpp: one type byte in front of every full block */,
+             CODEC_PEF = 5 /* not a block codec: 128-element windows of partitioned Elias-Fano sequences (pef.cuh) */, CODEC_ANY = 99 /* decided at run time from the index */ };
 
 constexpr uint32_t BLOCK = 128;            // BlockCodec::block_size for every codec
 constexpr uint32_t SCRATCH_WORDS = 32;     // interpolative stack: <= 7 pending right halves x 4 words

@@ -264,6 +264,10 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
             int rc = ix->pef->load(p, nbytes, codec, err);
             if (rc != 0) return fail(rc, err);
             ix->size = ix->pef->size; ix->num_docs = ix->pef->num_docs; ix->device_bytes = ix->pef->device_bytes;
+            // what the block-parallel query kernels see: the window directory in place of (block_max, endpoint)
+            ix->dev.lists = nullptr; ix->dev.dir = ix->pef->d_dir; ix->dev.bdir = ix->pef->d_bdir; ix->dev.bfirst = ix->pef->d_bfirst;
+            ix->dev.num_lists = ix->size; ix->dev.num_docs = uint32_t(ix->num_docs); ix->dev.codec = CODEC_PEF;
+            ix->dev.pdocs = ix->pef->dev.docs; ix->dev.pfreqs = ix->pef->dev.freqs;
             *out = ix.release();
             return DS2I_OK;
         }
@@ -338,6 +342,10 @@ extern "C" uint64_t ds2i_gpu_index_device_bytes(const ds2i_gpu_index* ix) { retu
 
 static inline uint64_t list_size_of(const ds2i_gpu_index* ix, uint32_t term) {
     return ix->kind == KIND_PEF ? ix->pef->host_dir[term].n : ix->host_dir[term].n;
+}
+// 128-posting blocks of a list as the block-parallel kernels count them (Elias-Fano lists: windows never straddle partitions)
+static inline uint64_t list_blocks_of(const ds2i_gpu_index* ix, uint32_t term) {
+    return ix->kind == KIND_PEF ? ix->pef->host_dir[term].blocks : (uint64_t(ix->host_dir[term].n) + BLOCK - 1) / BLOCK;
 }
 
 extern "C" int ds2i_gpu_index_set_global_stats(ds2i_gpu_index* ix, const uint64_t* df, size_t nterms, uint64_t num_docs_total) {
@@ -477,7 +485,7 @@ struct prep_part {
 
 static void prepare_range(const ds2i_gpu_index* ix, const ds2i_gpu_wand* wand, const uint32_t* terms, const uint64_t* query_offsets,
                           size_t q0, size_t q1, prep_part& out) {
-    struct ent { uint64_t n; float mw; uint8_t pos; uint64_t local_n; };   // n: the list size the reference would see (collection-wide df for a shard)
+    struct ent { uint64_t n; float mw; uint8_t pos; uint64_t local_n; uint32_t term; };   // n: the list size the reference would see (collection-wide df for a shard)
     std::vector<uint32_t> tmp;
     ent ents[MAX_TERMS], by_size[MAX_TERMS], by_mw[MAX_TERMS];
     out.nt.reserve(q1 - q0); out.cost.reserve(q1 - q0); out.shortest.reserve(q1 - q0);
@@ -503,7 +511,7 @@ static void prepare_range(const ds2i_gpu_index* ix, const ds2i_gpu_wand* wand, c
                 out.err = "query " + std::to_string(q) + " has more than " + std::to_string(MAX_TERMS) + " distinct terms";
                 return;
             }
-            ents[ne] = ent{n, mw, uint8_t(ne), local_n};
+            ents[ne] = ent{n, mw, uint8_t(ne), local_n, t};
             ++ne;
             out.term.push_back(t); out.q_weight.push_back(qw); out.max_weight.push_back(mw);
             cost += local_n;
@@ -517,7 +525,7 @@ static void prepare_range(const ds2i_gpu_index* ix, const ds2i_gpu_wand* wand, c
         std::sort(by_mw, by_mw + ne, [](ent const& l, ent const& r) { return l.mw < r.mw; });
         for (uint32_t i = 0; i < ne; ++i) { out.ord_size.push_back(by_size[i].pos); out.ord_maxw.push_back(by_mw[i].pos); }
         out.cost.push_back(cost);
-        out.shortest.push_back(ne ? by_size[0].local_n : 0);
+        out.shortest.push_back(ne ? list_blocks_of(ix, by_size[0].term) : 0);            // blocks of the driving list
     }
 }
 
@@ -613,7 +621,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         uint64_t nitems = 0;
         item_begin[0] = 0; and_gstart[0] = 0;
         for (size_t q = 0; q < nq; ++q) {
-            if (which & 1u) nitems += ((shortest[q] + BLOCK - 1) / BLOCK + and_chunk - 1) / and_chunk;
+            if (which & 1u) nitems += (shortest[q] + and_chunk - 1) / and_chunk;
             if (nitems > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many work items in one batch");
             item_begin[q + 1] = uint32_t(nitems);
         }
@@ -649,7 +657,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
                 acc = i ? acc + mw : mw;
                 ub[t0 + i] = acc;
                 if (!(which & 2u)) continue;
-                const uint64_t nb = (list_size_of(ix, term[t0 + ord_maxw[t0 + i]]) + BLOCK - 1) / BLOCK;
+                const uint64_t nb = list_blocks_of(ix, term[t0 + ord_maxw[t0 + i]]);
                 gchunks[t0 + i] = uint32_t((nb + item_blocks - 1) / item_blocks);
                 gbase[t0 + i] = uint32_t(nitems);
                 nitems += gchunks[t0 + i];
@@ -846,7 +854,12 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     CUDA_TRY(cudaEventRecord(b->ev0));
     int rc = DS2I_OK;
     if (b->nq) {
-        if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
+        const bool fast = !(flags & DS2I_RUN_FAITHFUL);
+        if (ix->kind == KIND_PEF && fast && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u))
+            rc = op == OP_AND ? launch_and_block<CODEC_PEF, false>(b, db, k) : launch_and_block<CODEC_PEF, true>(b, db, k);
+        else if (ix->kind == KIND_PEF && fast && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u))
+            rc = launch_union_block<CODEC_PEF>(b, db, k);
+        else if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
             rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k) : launch_and_block_codec<true>(b, db, k);
         }

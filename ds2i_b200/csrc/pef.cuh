@@ -19,12 +19,29 @@
 
 namespace ds2i_gpu {
 
-struct PefPart {            // one partition of one sequence
+struct PefPart {            // one partition of one sequence (32 bytes: two 16-byte loads)
     uint64_t bit_off;       // absolute bit offset of the partition body (its type bit, when present)
     uint32_t begin;         // position of its first element inside the list
     uint32_t size;          // elements
     uint32_t base;          // value offset: stored values are relative to it
     uint32_t ub;            // its last value (absolute)
+    uint32_t first_block;   // docs sequences: number of 128-element windows ("blocks") of the list before this partition
+    uint32_t body_bits;     // bits of the body (type bit included): what a staged copy has to cover
+};
+static_assert(sizeof(PefPart) == 32, "PefPart layout");
+
+// Where a decoder reads the bit vector from: HBM directly, or a window of it that TMA staged into shared memory
+// (the words of the window sit at smem[0 .. nw), word w0 of the vector first; reads outside the window give 0 — the
+// 32-words-per-step scans look past the end of a body, what they find there is never selected).
+struct GlobalBits {
+    const uint64_t* p;
+    __device__ __forceinline__ uint64_t word(uint64_t w) const { return __ldg(p + w); }
+};
+struct StagedBits {
+    const uint64_t* smem;
+    uint64_t w0;
+    uint32_t nw;
+    __device__ __forceinline__ uint64_t word(uint64_t w) const { const uint64_t i = w - w0; return i < nw ? smem[i] : 0ull; }
 };
 
 struct PefListDir {
@@ -52,20 +69,22 @@ enum : uint32_t { PEF_EF = 0, PEF_RB = 1, PEF_AO = 2 };
 __device__ __forceinline__ uint32_t ceil_log2_dev(uint64_t x) { return x > 1 ? 64u - uint32_t(__clzll(x - 1)) : 0u; }
 
 // bits [pos, pos+len) of the vector, len <= 32
-__device__ __forceinline__ uint32_t bv_get_bits(const uint64_t* bits, uint64_t pos, uint32_t len) {
+template <class Bits>
+__device__ __forceinline__ uint32_t bv_get_bits(Bits const& bits, uint64_t pos, uint32_t len) {
     if (!len) return 0u;
-    uint64_t w = __ldg(bits + (pos >> 6));
+    uint64_t w = bits.word(pos >> 6);
     uint32_t sh = uint32_t(pos & 63);
     uint64_t v = w >> sh;
-    if (sh + len > 64) v |= __ldg(bits + (pos >> 6) + 1) << (64 - sh);
+    if (sh + len > 64) v |= bits.word((pos >> 6) + 1) << (64 - sh);
     return uint32_t(v) & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u));
 }
-__device__ __forceinline__ uint64_t bv_get_bits64(const uint64_t* bits, uint64_t pos, uint32_t len) {   // len <= 57
+template <class Bits>
+__device__ __forceinline__ uint64_t bv_get_bits64(Bits const& bits, uint64_t pos, uint32_t len) {   // len <= 57
     if (!len) return 0ull;
-    uint64_t w = __ldg(bits + (pos >> 6));
+    uint64_t w = bits.word(pos >> 6);
     uint32_t sh = uint32_t(pos & 63);
     uint64_t v = w >> sh;
-    if (sh + len > 64) v |= __ldg(bits + (pos >> 6) + 1) << (64 - sh);
+    if (sh + len > 64) v |= bits.word((pos >> 6) + 1) << (64 - sh);
     return v & ((uint64_t(1) << len) - 1);
 }
 
@@ -91,7 +110,8 @@ struct PefBody {
 };
 
 // indexed_sequence / strict_sequence dispatch (indexed_sequence.hpp:95-127, strict_sequence.hpp:104-137)
-__device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart const& p, bool strict) {
+template <class Bits>
+__device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, Bits const& bits, PefPart const& p, bool strict) {
     PefBody b;
     b.n = p.size;
     b.universe = p.ub - p.base + 1u;            // last relative value + 1
@@ -100,7 +120,7 @@ __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart cons
     if (seq.raw_ef) b.type = PEF_EF;            // compact_elias_fano.hpp:63-136 / strict_elias_fano.hpp:20-36 written directly
     else {
         if (b.universe == b.n) { b.type = PEF_AO; return b; }
-        b.type = uint32_t(__ldg(seq.bits + (p.bit_off >> 6)) >> (p.bit_off & 63)) & 1u;
+        b.type = uint32_t(bits.word(p.bit_off >> 6) >> (p.bit_off & 63)) & 1u;
         off += 1;
     }
     if (b.type == PEF_EF) {
@@ -135,14 +155,15 @@ __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart cons
 
 // Positions (relative to `origin`) of the set bits with ordinals r0 .. r0+cnt-1 (ordinal 0 = first
 // set bit at or after `start`), cnt <= 128, written to out[0..cnt).  32 words per step.
-__device__ __forceinline__ void pef_scan_ones(const uint64_t* bits, uint64_t start, uint64_t origin, uint32_t r0, uint32_t cnt, uint32_t* out) {
+template <class Bits>
+__device__ __forceinline__ void pef_scan_ones(Bits const& bits, uint64_t start, uint64_t origin, uint32_t r0, uint32_t cnt, uint32_t* out) {
     const unsigned lane = lane_id();
     uint64_t wbase = start >> 6;
     uint32_t seen = 0;                    // set bits before the words of this step
     const uint32_t r1 = r0 + cnt;
     bool first = true;
     while (seen < r1) {
-        uint64_t w = __ldg(bits + wbase + lane);
+        uint64_t w = bits.word(wbase + lane);
         if (first && lane == 0) w &= ~uint64_t(0) << (start & 63);
         first = false;
         uint32_t pc = __popcll(w);
@@ -179,13 +200,14 @@ __device__ __forceinline__ void pef_scan_ones(const uint64_t* bits, uint64_t sta
 
 // count of ZERO bits wanted: position (relative to origin) of the zero with ordinal z (0 = first zero
 // at or after start), z < 2^log_sampling0 + slack.  Returns warp-uniformly.
-__device__ __forceinline__ uint64_t pef_select_zero(const uint64_t* bits, uint64_t start, uint32_t z) {
+template <class Bits>
+__device__ __forceinline__ uint64_t pef_select_zero(Bits const& bits, uint64_t start, uint32_t z) {
     const unsigned lane = lane_id();
     uint64_t wbase = start >> 6;
     uint32_t seen = 0;
     bool first = true;
     while (true) {
-        uint64_t w = ~__ldg(bits + wbase + lane);
+        uint64_t w = ~bits.word(wbase + lane);
         if (first && lane == 0) w &= ~uint64_t(0) << (start & 63);
         first = false;
         uint32_t pc = __popcll(w);
@@ -205,7 +227,8 @@ __device__ __forceinline__ uint64_t pef_select_zero(const uint64_t* bits, uint64
 }
 
 // Elements [i0, i0+cnt) of a partition (cnt <= 128) as ABSOLUTE values (base added) into out[0..cnt).
-__device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out) {
+template <class Bits>
+__device__ __forceinline__ void pef_decode_range(Bits const& bits, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out) {
     const unsigned lane = lane_id();
     if (b.type == PEF_AO) {
 #pragma unroll
@@ -221,18 +244,18 @@ __device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart cons
         uint64_t start = b.high_off;
         uint32_t r0 = i0;
         if (s) {
-            uint64_t ptr = bv_get_bits64(seq.bits, b.pointers1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
+            uint64_t ptr = bv_get_bits64(bits, b.pointers1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
             start = b.high_off + ptr;                      // high-bit position of element s << log_s1
             r0 = i0 - (s << b.log_s1);
         }
-        pef_scan_ones(seq.bits, start, b.high_off, r0, cnt, out);
+        pef_scan_ones(bits, start, b.high_off, r0, cnt, out);
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
             uint32_t e = lane + 32u * j;
             if (e < cnt) {
                 uint32_t i = i0 + e;
                 uint32_t high = out[e] - i - 1u;
-                uint32_t low = bv_get_bits(seq.bits, b.low_off + uint64_t(i) * b.lower_bits, b.lower_bits);
+                uint32_t low = bv_get_bits(bits, b.low_off + uint64_t(i) * b.lower_bits, b.lower_bits);
                 uint32_t v = (high << b.lower_bits) | low;
                 if (b.strict) v += i;                      // strict_elias_fano.hpp:50-60
                 out[e] = p.base + v;
@@ -242,11 +265,11 @@ __device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart cons
         uint64_t start = b.bitmap_off;
         uint32_t r0 = i0;
         if (s) {
-            uint64_t ptr = bv_get_bits64(seq.bits, b.rb_ptr1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
+            uint64_t ptr = bv_get_bits64(bits, b.rb_ptr1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
             start = b.bitmap_off + ptr;                    // value of element s << log_s1 = its bit position
             r0 = i0 - (s << b.log_s1);
         }
-        pef_scan_ones(seq.bits, start, b.bitmap_off, r0, cnt, out);
+        pef_scan_ones(bits, start, b.bitmap_off, r0, cnt, out);
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
             uint32_t e = lane + 32u * j;
@@ -259,7 +282,8 @@ __device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart cons
 // Index of the first element whose high part is >= (x >> l) (EF) / whose value is >= x (bitvector,
 // all-ones): a lower bound for the rank of x; for EF the caller refines by comparing decoded values.
 // x is relative to the partition base, x < universe.
-__device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody const& b, uint32_t x) {
+template <class Bits>
+__device__ __forceinline__ uint32_t pef_rank_hint(Bits const& bits, PefBody const& b, uint32_t x) {
     if (b.type == PEF_AO) return x;
     if (b.type == PEF_EF) {
         uint32_t high = x >> b.lower_bits;
@@ -269,11 +293,11 @@ __device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody con
         uint64_t start = b.high_off;
         uint32_t skip = high;
         if (k) {
-            uint64_t ptr = bv_get_bits64(seq.bits, b.pointers0_off + uint64_t(k - 1) * b.pointer_size, b.pointer_size);
+            uint64_t ptr = bv_get_bits64(bits, b.pointers0_off + uint64_t(k - 1) * b.pointer_size, b.pointer_size);
             start = b.high_off + ptr;
             skip = high - (k << b.log_s0);
         }
-        uint64_t z = pef_select_zero(seq.bits, start, skip);
+        uint64_t z = pef_select_zero(bits, start, skip);
         return uint32_t(z - b.high_off) - high;
     }
     // ranked bitvector: ones in [0, x) = sample + popcount of the remainder (compact_ranked_bitvector.hpp:256-302)
@@ -283,7 +307,7 @@ __device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody con
     uint32_t rank = 0;
     uint64_t from = b.bitmap_off;
     if (k) {
-        rank = uint32_t(bv_get_bits64(seq.bits, b.rank_off + uint64_t(k - 1) * b.rank_sample_size, b.rank_sample_size));
+        rank = uint32_t(bv_get_bits64(bits, b.rank_off + uint64_t(k - 1) * b.rank_sample_size, b.rank_sample_size));
         from = b.bitmap_off + (uint64_t(k) << b.log_s0);
     }
     const uint64_t to = b.bitmap_off + x;
@@ -292,13 +316,30 @@ __device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody con
         uint64_t wi = wb + lane;
         uint64_t w = 0;
         if (wi * 64 < to) {
-            w = __ldg(seq.bits + wi);
+            w = bits.word(wi);
             if (wi == (from >> 6)) w &= ~uint64_t(0) << (from & 63);
             if ((wi + 1) * 64 > to) w &= (uint64_t(1) << (to & 63)) - 1;
         }
         acc += __popcll(w);
     }
     return rank + __reduce_add_sync(FULL, acc);
+}
+
+// the same straight from HBM (what the literal enumerator and the full-decode kernels use)
+__device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart const& p, bool strict) { return pef_open_body(seq, GlobalBits{seq.bits}, p, strict); }
+__device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out) {
+    pef_decode_range(GlobalBits{seq.bits}, p, b, i0, cnt, out);
+}
+__device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody const& b, uint32_t x) { return pef_rank_hint(GlobalBits{seq.bits}, b, x); }
+
+// one PefPart record: two 16-byte loads
+__device__ __forceinline__ PefPart pef_load_part(const PefPart* parts, uint64_t i) {
+    const uint4* q = reinterpret_cast<const uint4*>(parts + i);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    PefPart r;
+    r.bit_off = (uint64_t(a.y) << 32) | a.x; r.begin = a.z; r.size = a.w;
+    r.base = b.x; r.ub = b.y; r.first_block = b.z; r.body_bits = b.w;
+    return r;
 }
 
 }  // namespace ds2i_gpu

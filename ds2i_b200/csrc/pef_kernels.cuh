@@ -44,14 +44,7 @@ struct PefEnum {
     typedef PefState State;
     typedef PefIndexDev Index;
 
-    static __device__ __forceinline__ PefPart load_part(const PefPart* parts, uint64_t i) {
-        PefPart r;
-        const uint64_t* q = reinterpret_cast<const uint64_t*>(parts + i);       // 24-byte records, 8-byte aligned
-        r.bit_off = __ldg(q);
-        uint64_t a = __ldg(q + 1), b = __ldg(q + 2);
-        r.begin = uint32_t(a); r.size = uint32_t(a >> 32); r.base = uint32_t(b); r.ub = uint32_t(b >> 32);
-        return r;
-    }
+    static __device__ __forceinline__ PefPart load_part(const PefPart* parts, uint64_t i) { return pef_load_part(parts, i); }
 
     // decode the chunk of partition `part` that starts at local index i0
     static __device__ __forceinline__ void load_chunk(Index const& idx, State* st, uint32_t part, uint32_t i0) {
@@ -443,9 +436,23 @@ static inline void pef_parse_any(int variant, bitvec_view const& bv, uint64_t of
     }
 }
 
+// block directory of the docs sequences: entry j of a list = (last docid of its j-th 128-element window, index of the window's
+// partition inside the list) — the analogue of the block indexes' (block_max, endpoint) directory, so the block-parallel
+// query kernels find a window of an Elias-Fano list with the same ballot search they use for block_max
+static __global__ void __launch_bounds__(256) pef_block_dir_kernel(const uint32_t* docs, const uint64_t* last_elem, const uint32_t* part_rel,
+                                                                   uint64_t nblocks, uint2* out) {
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < nblocks; j += uint64_t(gridDim.x) * blockDim.x)
+        out[j] = make_uint2(__ldg(docs + last_elem[j]), part_rel[j]);
+}
+
 struct PefIndexHost {
     uint64_t size = 0, num_docs = 0, device_bytes = 0;
-    struct host_list { uint64_t n; uint64_t bits; };      // postings; bits of the list in the docs + freqs bit vectors
+    uint2* d_bdir = nullptr;            // block directory (device), total_blocks + 1 entries
+    uint32_t* d_bfirst = nullptr;       // size + 1 entries: first block of every list
+    ListDir* d_dir = nullptr;           // per list: n (the other ListDir fields are unused by this index family)
+    uint64_t total_blocks = 0;
+    ~PefIndexHost() { if (d_bdir) cudaFree(d_bdir); if (d_bfirst) cudaFree(d_bfirst); if (d_dir) cudaFree(d_dir); }
+    struct host_list { uint64_t n; uint64_t bits; uint64_t blocks; };      // postings; bits of the list in the docs + freqs bit vectors; 128-element windows of the docs sequence
     std::vector<host_list> host_dir;
     PefSeqHost docs, freqs;
     PefIndexDev dev{};
@@ -463,6 +470,10 @@ struct PefIndexHost {
         s.device_bytes = words * 8 + s.lists.size() * sizeof(PefListDir) + s.parts.size() * sizeof(PefPart);
         return 0;
     }
+
+    // Decodes every docs sequence once on the device (chunks of lists, so the scratch stays bounded) and keeps the last
+    // docid of every 128-element window.  Load-time work, like the (block_max, endpoint) directory of the block indexes.
+    int build_block_directory(std::string& err);
 
     // freq_index::map (freq_index.hpp:234-243) + per-list headers (freq_index.hpp:192-214)
     int load(const uint8_t* p, size_t nbytes, int variant, std::string& err) {
@@ -496,6 +507,23 @@ struct PefIndexHost {
                 freqs.lists[i] = PefListDir{freqs.parts.size(), 0u, uint32_t(n)};
                 pef_parse_any(variant, fbits, fstart[i], occurrences + 1, n, gp, freqs.parts);
                 freqs.lists[i].nparts = uint32_t(freqs.parts.size() - freqs.lists[i].first_part);
+                // windows before each docs partition, and how many bits each body spans (bodies are back to back)
+                auto finish = [&](PefSeqHost& sq, uint64_t list_end_bit) {
+                    uint64_t fb = 0;
+                    for (uint64_t k = sq.lists[i].first_part; k < sq.parts.size(); ++k) {
+                        PefPart& pp = sq.parts[k];
+                        pp.first_block = uint32_t(fb);
+                        fb += (uint64_t(pp.size) + 127) / 128;
+                        const uint64_t end = k + 1 < sq.parts.size() ? sq.parts[k + 1].bit_off : list_end_bit;
+                        pp.body_bits = end > pp.bit_off && end - pp.bit_off < 0xffffffffull ? uint32_t(end - pp.bit_off) : 0u;
+                    }
+                    return fb;
+                };
+                const uint64_t nb = finish(docs, i + 1 < size ? dstart[i + 1] : dbits.bits);
+                finish(freqs, i + 1 < size ? fstart[i + 1] : fbits.bits);
+                if (total_blocks + nb > 0xfffffff0ull) throw format_error("more than 2^32 windows in the index");
+                total_blocks += nb;
+                host_dir[i].blocks = nb;
             }
             int rc = upload(docs, dbits, err);
             if (rc) return rc;
@@ -511,6 +539,8 @@ struct PefIndexHost {
             };
             dev.docs = mk(docs); dev.freqs = mk(freqs); dev.num_lists = size; dev.num_docs = uint32_t(num_docs);
             device_bytes = docs.device_bytes + freqs.device_bytes;
+            rc = build_block_directory(err);
+            if (rc) return rc;
         } catch (std::exception const& e) {
             err = e.what();
             return -2;
@@ -588,6 +618,78 @@ inline int pef_next_geq(PefIndexHost& ix, const uint32_t* d_terms, uint32_t nlis
     PefGeqJob job{d_terms, d_bounds, d_offsets, d_docids, d_freqs, d_counter, nlists};
     int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(nlists) + 3) / 4, uint64_t(sm_count) * 8)));
     pef_next_geq_kernel<<<grid, 128, 4 * sizeof(PefState)>>>(ix.dev, job);
+    return 0;
+}
+
+inline int PefIndexHost::build_block_directory(std::string& err) {
+    auto fail_cuda = [&](const char* what) { err = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()); return -3; };
+    std::vector<uint32_t> bfirst(size + 1, 0);
+    std::vector<ListDir> dir(size);
+    for (uint64_t i = 0; i < size; ++i) {
+        uint64_t nb = 0;
+        for (uint32_t k = 0; k < docs.lists[i].nparts; ++k) nb += (uint64_t(docs.parts[docs.lists[i].first_part + k].size) + 127) / 128;
+        bfirst[i + 1] = bfirst[i] + uint32_t(nb);
+        dir[i] = ListDir{0, uint32_t(host_dir[i].n), 0};
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&d_bdir), (total_blocks + 1) * sizeof(uint2)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&d_bfirst), (size + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&d_dir), std::max<uint64_t>(size, 1) * sizeof(ListDir)) != cudaSuccess) return fail_cuda("cudaMalloc (block directory)");
+    const uint2 sentinel = make_uint2(0xffffffffu, 0u);            // probes may read one entry past the last list
+    if (cudaMemcpy(d_bdir + total_blocks, &sentinel, sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_bfirst, bfirst.data(), (size + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_dir, dir.data(), size * sizeof(ListDir), cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("H2D copy (block directory)");
+    device_bytes += (total_blocks + 1) * sizeof(uint2) + (size + 1) * 4 + size * sizeof(ListDir);
+
+    const uint64_t chunk_postings = uint64_t(1) << 27;              // 512 MB of decoded docids at a time
+    std::vector<PefDecodeItem> items;
+    std::vector<uint32_t> terms, part_rel;
+    std::vector<uint64_t> offsets, last_elem;
+    for (uint64_t l0 = 0; l0 < size;) {
+        uint64_t l1 = l0, postings = 0;
+        while (l1 < size && (l1 == l0 || postings + host_dir[l1].n <= chunk_postings)) postings += host_dir[l1++].n;
+        items.clear(); terms.clear(); part_rel.clear(); offsets.clear(); last_elem.clear();
+        uint64_t at = 0;
+        for (uint64_t l = l0; l < l1; ++l) {
+            terms.push_back(uint32_t(l));
+            offsets.push_back(at);
+            PefListDir const& d = docs.lists[l];
+            for (uint32_t pi = 0; pi < d.nparts; ++pi) {
+                PefPart const& pp = docs.parts[d.first_part + pi];
+                for (uint32_t first = 0; first < pp.size; first += PEF_ITEM_ELEMS)
+                    items.push_back(PefDecodeItem{uint32_t(l - l0), pi, first, std::min(PEF_ITEM_ELEMS, pp.size - first)});
+                for (uint32_t w = 0; w * 128u < pp.size; ++w) {
+                    last_elem.push_back(at + pp.begin + std::min<uint64_t>(pp.size, 128ull * (w + 1)) - 1);
+                    part_rel.push_back(pi);
+                }
+            }
+            at += host_dir[l].n;
+        }
+        offsets.push_back(at);
+        const uint64_t nb = last_elem.size();
+        uint32_t *d_terms = nullptr, *d_docs = nullptr, *d_prel = nullptr;
+        uint64_t *d_offs = nullptr, *d_last = nullptr;
+        PefDecodeItem* d_items = nullptr;
+        auto cleanup = [&]() { cudaFree(d_terms); cudaFree(d_docs); cudaFree(d_prel); cudaFree(d_offs); cudaFree(d_last); cudaFree(d_items); };
+        if (cudaMalloc(reinterpret_cast<void**>(&d_terms), terms.size() * 4) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&d_docs), std::max<uint64_t>(at, 1) * 4) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&d_prel), std::max<uint64_t>(nb, 1) * 4) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&d_offs), offsets.size() * 8) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&d_last), std::max<uint64_t>(nb, 1) * 8) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&d_items), std::max<size_t>(items.size(), 1) * sizeof(PefDecodeItem)) != cudaSuccess) { cleanup(); return fail_cuda("cudaMalloc (block directory scratch)"); }
+        bool ok = cudaMemcpy(d_terms, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d_offs, offsets.data(), offsets.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d_prel, part_rel.data(), nb * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d_last, last_elem.data(), nb * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d_items, items.data(), items.size() * sizeof(PefDecodeItem), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok && !items.empty()) {
+            PefDecodeJob job{d_terms, d_items, d_offs, d_docs, nullptr, uint32_t(items.size())};
+            int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((items.size() + 7) / 8, 148ull * 8)));
+            pef_decode_kernel<<<grid, 256, 8 * 4096>>>(dev, job);
+            pef_block_dir_kernel<<<int(std::max<uint64_t>(1, std::min<uint64_t>((nb + 255) / 256, 148ull * 8))), 256>>>(d_docs, d_last, d_prel, nb, d_bdir + bfirst[l0]);
+            ok = cudaDeviceSynchronize() == cudaSuccess;
+        }
+        cleanup();
+        if (!ok) return fail_cuda("block directory build");
+        l0 = l1;
+    }
     return 0;
 }
 

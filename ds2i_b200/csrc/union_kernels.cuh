@@ -89,7 +89,7 @@ __device__ __forceinline__ void union_probe(AndCtx& c, DevIndex const& idx, AndL
             const bool fresh = cur_block == 0xffffffffu;
             const BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
                                                 fresh ? 0u : s->cur_end, cmin);
-            and_decode_docs<CODEC>(c, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
+            and_decode_docs<CODEC>(c, idx, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
         }
         const uint32_t cur_max = s->cur_max;
         const uint32_t* d = s->docs;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void union_probe(AndCtx& c, DevIndex const& idx, AndL
         }
         if (!score_mode) alive &= ~hitmask;
         else if (__any_sync(FULL, hitmask)) {
-            const bool prefix = and_decode_freqs<CODEC>(c, s, i, c.ftmp_off);
+            const bool prefix = and_decode_freqs<CODEC>(c, idx, s, i, c.ftmp_off);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (hitmask & (1u << j)) {
@@ -200,16 +200,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
             const uint32_t src = batch.ord_maxw[t0 + lane];
             ws->qw[lane] = batch.q_weight[t0 + src];
             ws->ub[lane] = __ldg(job.ub + t0 + lane) * INFLATE;
-            const uint32_t term = batch.term[t0 + src];
-            const ListDir d = idx.dir[term];
-            const uint32_t nblocks = (d.n + BLOCK - 1) / BLOCK;
-            const uint32_t bfirst = idx.bfirst[term];
-            AndList* s = &st[lane];
-            s->data_off = d.maxs_off + 4ull * nblocks + 4ull * (nblocks - 1);
-            s->bfirst = bfirst; s->nblocks = nblocks; s->n = d.n;
-            s->last_max = __ldg(idx.bdir + bfirst + nblocks - 1).x;
-            s->cur_block = 0xffffffffu;     // not positioned yet
-            s->cur_max = 0; s->cur_end = 0; s->freqs_off = 0;
+            and_list_setup<CODEC>(idx, &st[lane], batch.term[t0 + src]);
         }
         __syncwarp();
 
@@ -235,7 +226,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                 {
                     const uint32_t l = b0 - c0;
                     const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
-                    and_decode_docs<CODEC>(c, sd, e, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
+                    and_decode_docs<CODEC>(c, idx, sd, e, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
                                            __shfl_sync(FULL, m_max, l));
                 }
                 const uint4 cv = reinterpret_cast<const uint4*>(sd->docs)[lane];
@@ -253,7 +244,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (alive & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
-                        const bool prefix = and_decode_freqs<CODEC>(c, sd, e, c.ftmp_off);
+                        const bool prefix = and_decode_freqs<CODEC>(c, idx, sd, e, c.ftmp_off);
                         const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
                         uint32_t f0[4] = {fv.x, fv.y, fv.z, fv.w};
                         if (prefix) {
