@@ -183,7 +183,7 @@ class QueryBatch:
         _native.check(_native.lib().ds2i_gpu_batch_prepare(index._h, wh, _p(flat, C.c_uint32), _p(offs, C.c_uint64), self.nq, C.byref(self._h)))
         self.h2d_bytes = flat.nbytes + offs.nbytes
 
-    def run(self, op, k=10, faithful=False, wait=True):
+    def run(self, op, k=10, faithful=False, wait=True, stats=True):
         """Evaluate `op` over the resident batch; returns the CUDA-event time in ms.  faithful=True
         selects the literal one-candidate-at-a-time kernels (DS2I_RUN_FAITHFUL).  wait=False launches
         without a host synchronisation (DS2I_RUN_ASYNC): the work is ordered on the device's default
@@ -191,7 +191,7 @@ class QueryBatch:
         ms = C.c_float()
         self._k = k
         self._op = op
-        flags = (1 if faithful else 0) | (0 if wait else 2)
+        flags = (1 if faithful else 0) | (0 if wait else 2) | (0 if stats else 4)        # stats=False: DS2I_RUN_NO_STATS
         _native.check(_native.lib().ds2i_gpu_batch_run_ex(self._h, OPS.index(op), k, flags, C.byref(ms)))
         return ms.value
 

@@ -16,16 +16,17 @@
 // buffer) and the kernel is instantiated per codec, because the path is instruction-issue bound:
 // resident warps and instruction count are what the throughput follows.
 #pragma once
+#include <type_traits>
+
 #include "query_kernels.cuh"
 
 namespace ds2i_gpu {
 
-// algorithmic-work counters can be compiled out (-DDS2I_NO_STATS) to measure what they cost
-#ifdef DS2I_NO_STATS
-#define DS2I_STAT(x)
-#else
-#define DS2I_STAT(x) x
-#endif
+// algorithmic-work counters
+// Every use site has the warp context in a variable `c`; AndCtxT<false> compiles the counters away (the timed launches of the
+// benchmark run without them — they cost registers in kernels that are register-bound — and one more, instrumented launch of
+// the same batch collects them: the algorithmic work of a batch does not depend on the instance that measures it).
+#define DS2I_STAT(x) if constexpr (std::remove_reference_t<decltype(c)>::stats) { x }
 
 #ifdef DS2I_NIN_HIST
 // experiment: distribution of the probe regimes.  [0..7] probe steps by candidates answered (1, 2-3, 4-7, .., 64-128), [8] driver blocks,
@@ -93,8 +94,19 @@ struct AndWarp {
     uint64_t pad;
 };
 
-__host__ __device__ constexpr size_t and_warp_smem_bytes(int slots) {
-    return sizeof(AndWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + STAGE_WORDS * 4 + SCRATCH_WORDS * 4;
+// Elias-Fano path: the partition of the freqs sequence a list's last freqs window came from (lists are walked forward and
+// freqs partitions are long, so the next window nearly always hits it: no directory search, no descriptor loads)
+struct PefFreqSlot {
+    PefPart part;
+    uint32_t fp;            // index of the partition inside the list's freqs sequence; 0xffffffff: nothing cached
+    uint32_t type;          // its type bit
+    uint32_t pad[6];
+};
+static_assert(sizeof(PefFreqSlot) == 64, "PefFreqSlot layout");
+
+__host__ __device__ constexpr size_t and_warp_smem_bytes(int slots, bool pef = false) {
+    return sizeof(AndWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 +
+           (pef ? size_t(slots) * sizeof(PefFreqSlot) : 0);
 }
 
 // staging window <- bytes [start, end) of m_lists (the enclosing 16-B aligned range, one TMA bulk copy,
@@ -156,102 +168,109 @@ __device__ __forceinline__ void and_list_setup(DevIndex const& idx, AndList* s, 
     s->cur_max = 0; s->cur_end = 0; s->freqs_off = 0;
 }
 
-struct AndCtx {             // warp-uniform registers
+template <bool STATS>
+struct AndCtxT {            // warp-uniform registers
+    static constexpr bool stats = STATS;
     const uint8_t* lists;
     uint32_t* stage;
     uint64_t* bar;
     uint32_t stage_off, stack_off, ftmp_off;
+    uint32_t fcache_off;    // Elias-Fano path: the warp's PefFreqSlot array
     uint32_t phase;
     uint32_t win_slot;      // list slot whose current block pair sits in the staging window (0xffffffff: none)
     uint32_t win_delta;     // window offset of that list's data byte 0 (mod 2^32)
     // algorithmic-work counters
     uint32_t c_docs_blocks, c_freqs_blocks, c_bytes_docs, c_bytes_freqs, c_maxs, c_scored;
 };
+typedef AndCtxT<true> AndCtx;
 
 // ---- Elias-Fano index family: a "block" is a 128-element window of one partition of the docs sequence --------------------
 // Window b of the list -> its partition (the directory's second word: index of the partition inside the list) and the
 // elements [128 w, 128 w + 128) of it.  A body of up to STAGE_BYTES is copied into the warp's staging window with one TMA
 // bulk copy and decoded from shared memory (both windows of a two-window partition reuse the copy); longer bodies (the
-// single-partition sequences of very regular lists) are read in place.
-template <class List>
-__device__ __forceinline__ void pef_window_docs(AndCtx& c, DevIndex const& idx, List* s, uint32_t slot, uint32_t b, uint32_t part_rel, uint32_t cur_max) {
+// single-partition sequences of very regular lists) are read in place.  De-inlined, scalars in and out: the kernels call it
+// from two sites each and the code around the decoder is not small either (the kernels were instruction-fetch bound).
+struct PefDocsWindow { uint32_t phase, staged_part, first_pos, cnt; };
+
+__device__ __noinline__ PefDocsWindow pef_window_docs(PefSeq seq, uint64_t first_part, uint32_t b, uint32_t part_rel, uint32_t stage_off, uint32_t bar_off,
+                                                      uint32_t phase, uint32_t staged_part /* partition in the staging window, 0xffffffff: none */, uint32_t docs_off) {
     const unsigned lane = lane_id();
-    const PefPart p = pef_load_part(idx.pdocs.parts, s->data_off + part_rel);
+    const PefPart p = pef_load_part(seq.parts, first_part + part_rel);
     const uint32_t i0 = (b - p.first_block) * BLOCK;
     const uint32_t cnt = min(BLOCK, p.size - i0);
     const uint64_t byte0 = (p.bit_off >> 3) & ~uint64_t(15);
     const uint64_t byte1 = (((p.bit_off + p.body_bits + 7) >> 3) + 15) & ~uint64_t(15);
+    AnyBits bits{seq.bits, 0, 0, 0};
     if (p.body_bits && byte1 - byte0 <= STAGE_BYTES) {
-        if (!(c.win_slot == slot && c.win_delta == part_rel)) {
+        if (staged_part != part_rel) {
+            uint64_t* bar = reinterpret_cast<uint64_t*>(g_smem + bar_off);
             __syncwarp();   // every lane is done reading the previous window
             if (lane == 0) {
-                mbar_expect_tx(c.bar, uint32_t(byte1 - byte0));
-                tma_load_1d(c.stage, reinterpret_cast<const uint8_t*>(idx.pdocs.bits) + byte0, uint32_t(byte1 - byte0), c.bar);
+                mbar_expect_tx(bar, uint32_t(byte1 - byte0));
+                tma_load_1d(g_smem + stage_off, reinterpret_cast<const uint8_t*>(seq.bits) + byte0, uint32_t(byte1 - byte0), bar);
             }
-            mbar_wait(c.bar, c.phase);
-            c.phase ^= 1u;
-            c.win_slot = slot; c.win_delta = part_rel;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            staged_part = part_rel;
         }
-        const StagedBits sb{reinterpret_cast<const uint64_t*>(c.stage), byte0 >> 3, uint32_t((byte1 - byte0) >> 3)};
-        const PefBody body = pef_open_body(idx.pdocs, sb, p, false);
-        pef_decode_range(sb, p, body, i0, cnt, s->docs);
-        DS2I_STAT(c.c_bytes_docs += (cnt * (p.body_bits >> 3)) / p.size;)
-    } else {
-        const GlobalBits gb{idx.pdocs.bits};
-        const PefBody body = pef_open_body(idx.pdocs, gb, p, false);
-        pef_decode_range(gb, p, body, i0, cnt, s->docs);
-        DS2I_STAT(c.c_bytes_docs += p.body_bits ? uint32_t((uint64_t(cnt) * (p.body_bits >> 3)) / p.size) : cnt;)
+        bits.w0 = byte0 >> 3; bits.smem_off = stage_off; bits.nw = uint32_t((byte1 - byte0) >> 3);
     }
+    pef_window_values(pef_params(seq), bits, p, false, i0, cnt, docs_off, false);
+    uint32_t* docs = smem_words(docs_off);
 #pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) { const uint32_t e = lane + 32u * j; if (e >= cnt) s->docs[e] = 0xffffffffu; }
-    // cur_end: the window's partition; freqs_off: list position of the window's first element
-    if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, part_rel, p.begin + i0);
+    for (uint32_t j = 0; j < 4; ++j) { const uint32_t e = lane + 32u * j; if (e >= cnt) docs[e] = 0xffffffffu; }
     __syncwarp();
-    DS2I_STAT(c.c_docs_blocks += 1;)
+    return PefDocsWindow{phase, staged_part, p.begin + i0, cnt};
 }
 
-// freq() - 1 of the postings of the current window of `s` -> the 128-word buffer at out.  positive_sequence over the strict
+// freq() - 1 of the postings at list positions [g0, g0 + cnt) -> the 128-word buffer at out_off.  positive_sequence over the strict
 // prefix sums c[] (positive_sequence.hpp:48-66): freq(i) = c[i] - c[i-1].  The freqs sequence has its own partitions; a docs
 // window may straddle two of them, so the range is decoded partition by partition.
-template <class List>
-__device__ __forceinline__ void pef_window_freqs(AndCtx& c, DevIndex const& idx, const List* s, uint32_t* out) {
+__device__ __noinline__ void pef_window_freqs(PefSeq seq, uint32_t term, uint32_t g0, uint32_t cnt, uint32_t fcache_slot_off, uint32_t out_off) {
     const unsigned lane = lane_id();
-    const uint32_t b = s->cur_block;
-    const uint32_t g0 = s->freqs_off;                                   // list position of the window's first element
-    const PefPart dp = pef_load_part(idx.pdocs.parts, s->data_off + s->cur_end);
-    const uint32_t cnt = min(BLOCK, dp.size - (b - dp.first_block) * BLOCK);
-    const PefListDir fl = idx.pfreqs.lists[s->term];
-    const GlobalBits gb{idx.pfreqs.bits};
-    // partition of the freqs sequence holding position g0: last partition with begin <= g0 (32 probes per step)
-    uint32_t lo = 0, hi = fl.nparts;
-    while (hi - lo > 1) {
-        const uint32_t span = hi - lo, step = (span + 31u) / 32u, pi = lo + lane * step;
-        const bool le = pi < hi && __ldg(reinterpret_cast<const uint32_t*>(idx.pfreqs.parts + fl.first_part + pi) + 2) <= g0;      // PefPart::begin
-        const unsigned m = __ballot_sync(FULL, le);
-        const uint32_t f = 31u - __clz(m);
-        lo = lo + f * step;
-        hi = min(hi, lo + step);
+    uint32_t* out = smem_words(out_off);
+    const AnyBits gb{seq.bits, 0, 0, 0};
+    PefFreqSlot* fc = reinterpret_cast<PefFreqSlot*>(g_smem + fcache_slot_off);
+    uint32_t fp = fc->fp;
+    PefPart p = fc->part;
+    uint32_t type = fc->type;
+    uint64_t first_part = 0;
+    bool have_first = false;
+    bool cached = fp != 0xffffffffu && g0 >= p.begin && g0 - p.begin < p.size;
+    if (!cached) {
+        // partition of the freqs sequence holding position g0: last partition with begin <= g0 (32 probes per step)
+        const PefListDir fl = seq.lists[term];
+        first_part = fl.first_part; have_first = true;
+        uint32_t lo = 0, hi = fl.nparts;
+        while (hi - lo > 1) {
+            const uint32_t span = hi - lo, step = (span + 31u) / 32u, pi = lo + lane * step;
+            const bool le = pi < hi && __ldg(reinterpret_cast<const uint32_t*>(seq.parts + fl.first_part + pi) + 2) <= g0;      // PefPart::begin
+            const unsigned m = __ballot_sync(FULL, le);
+            const uint32_t f = 31u - __clz(m);
+            lo = lo + f * step;
+            hi = min(hi, lo + step);
+        }
+        fp = lo;
     }
-    uint32_t fp = lo, g = g0, prev = 0;
+    uint32_t g = g0, prev = 0;
     bool have_prev = false;
     while (g < g0 + cnt) {
-        const PefPart p = pef_load_part(idx.pfreqs.parts, fl.first_part + fp);
-        const PefBody body = pef_open_body(idx.pfreqs, gb, p, true);
+        if (!cached) {
+            if (!have_first) { first_part = seq.lists[term].first_part; have_first = true; }       // a window that runs past the cached partition
+            p = pef_load_part(seq.parts, first_part + fp);
+            type = (seq.raw_ef || p.ub - p.base + 1u == p.size) ? 0u : uint32_t(gb.word(p.bit_off >> 6) >> (p.bit_off & 63)) & 1u;
+            __syncwarp();
+            if (lane == 0) { fc->part = p; fc->fp = fp; fc->type = type; }
+        }
         const uint32_t local = g - p.begin;
         const uint32_t take = min(g0 + cnt - g, p.size - local);
-        if (!have_prev) {
-            // c[g0 - 1]: the value before a partition's first element is the previous partition's last value = base - 1
-            // (partition 0: the sum before the first element is 0); otherwise one more element is decoded
-            if (local == 0) prev = fp ? p.base - 1u : 0u;
-            else {
-                pef_decode_range(gb, p, body, local - 1u, 1u, out);
-                prev = out[0];
-                __syncwarp();
-            }
-            have_prev = true;
-        }
-        pef_decode_range(gb, p, body, local, take, out + (g - g0));
+        // c[g0 - 1]: the value before a partition's first element is the previous partition's last value = base - 1
+        // (partition 0: the sum before the first element is 0); otherwise the element before the window is decoded along
+        const bool need_prev = !have_prev && local != 0;
+        const uint32_t pv = pef_window_values(pef_params(seq), gb, p, true, local, take, out_off + 4u * (g - g0), need_prev, type);
+        if (!have_prev) { prev = local ? pv : (fp ? p.base - 1u : 0u); have_prev = true; }
         g += take; ++fp;
+        cached = false;
     }
     // prefix sums -> freq - 1, in place
     uint32_t v[5];
@@ -263,16 +282,22 @@ __device__ __forceinline__ void pef_window_freqs(AndCtx& c, DevIndex const& idx,
     r.x = v[1] - v[0] - 1u; r.y = v[2] - v[1] - 1u; r.z = v[3] - v[2] - 1u; r.w = v[4] - v[3] - 1u;
     reinterpret_cast<uint4*>(out)[lane] = r;
     __syncwarp();
-    DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += cnt;)
 }
 
 // block_posting_list.hpp:292-319 with the block's metadata in hand: [e0, e1) = byte range of the block
 // pair inside the list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
-template <int CODEC, class List>
-__device__ __forceinline__ void and_decode_docs(AndCtx& c, DevIndex const& idx, List* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
+template <int CODEC, class List, class Ctx>
+__device__ __forceinline__ void and_decode_docs(Ctx& c, DevIndex const& idx, List* s, uint32_t slot, uint32_t b, uint32_t e0, uint32_t e1, uint32_t prev_max, uint32_t cur_max) {
     if constexpr (CODEC == CODEC_PEF) {
         (void)e0; (void)prev_max;
-        pef_window_docs(c, idx, s, slot, b, e1, cur_max);
+        const PefDocsWindow w = pef_window_docs(idx.pdocs, s->data_off, b, e1, c.stage_off, smem_offset(c.bar), c.phase,
+                                                c.win_slot == slot ? c.win_delta : 0xffffffffu, smem_offset(s->docs));
+        c.phase = w.phase;
+        if (w.staged_part != 0xffffffffu) { c.win_slot = slot; c.win_delta = w.staged_part; }
+        // cur_end: the window's partition; freqs_off: list position of the window's first element; pad1: its size
+        if (lane_id() == 0) { *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, e1, w.first_pos); s->pad1 = w.cnt; }
+        __syncwarp();
+        DS2I_STAT(c.c_docs_blocks += 1; c.c_bytes_docs += w.cnt;)
         return;
     }
     const unsigned lane = lane_id();
@@ -306,11 +331,11 @@ __device__ __forceinline__ void and_decode_docs(AndCtx& c, DevIndex const& idx, 
 // freqs - 1 of the current block of `s` -> the 128-word buffer at out_off.  Right after the docs decode the
 // block pair is still staged; a block carried over from an earlier candidate batch is staged again.
 // Returns whether the buffer holds prefix sums (interpolative) instead of plain values.
-template <int CODEC, class List>
-__device__ __forceinline__ bool and_decode_freqs(AndCtx& c, DevIndex const& idx, const List* s, uint32_t slot, uint32_t out_off) {
+template <int CODEC, class List, class Ctx>
+__device__ __forceinline__ bool and_decode_freqs(Ctx& c, DevIndex const& idx, const List* s, uint32_t slot, uint32_t out_off) {
     if constexpr (CODEC == CODEC_PEF) {
-        (void)slot;
-        pef_window_freqs(c, idx, s, smem_words(out_off));
+        pef_window_freqs(idx.pfreqs, s->term, s->freqs_off, s->pad1, c.fcache_off + slot * uint32_t(sizeof(PefFreqSlot)), out_off);
+        DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += s->pad1;)
         return false;
     }
     const uint32_t n = s->n, b = s->cur_block;
@@ -333,13 +358,14 @@ __device__ __forceinline__ bool and_decode_freqs(AndCtx& c, DevIndex const& idx,
 // arrive with the probe; longer skips run a 32-ary search first.
 struct BlockMeta { uint32_t block, e0, e1, prev_max, cur_max; };
 
-__device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint2* bd, uint32_t nblocks, uint32_t lo, uint32_t lo_prev_max, uint32_t lo_prev_end,
+template <class Ctx>
+__device__ __forceinline__ BlockMeta and_find_block(Ctx& c, const uint2* bd, uint32_t nblocks, uint32_t lo, uint32_t lo_prev_max, uint32_t lo_prev_end,
                                                     uint32_t bound) {
     const unsigned lane = lane_id();
     uint32_t bi = lo + lane;
     uint2 en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
     unsigned hit = __ballot_sync(FULL, en.x >= bound);
-    DS2I_STAT(c_maxs += 32;)
+    DS2I_STAT(c.c_maxs += 32;)
     if (!hit) {
         uint32_t l2 = lo + 32, hi = nblocks - 1;     // invariant: max[hi] >= bound, every block < l2 has max < bound
         while (hi - l2 >= 31) {
@@ -347,7 +373,7 @@ __device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint
             const uint32_t probe = l2 + uint32_t((uint64_t(span) * (lane + 1)) / 33);
             const uint32_t m = __ldg(bd + probe).x;
             const unsigned h = __ballot_sync(FULL, m >= bound);
-            DS2I_STAT(c_maxs += 32;)
+            DS2I_STAT(c.c_maxs += 32;)
             if (h) {
                 const uint32_t f = __ffs(h) - 1;
                 const uint32_t nh = __shfl_sync(FULL, probe, f);
@@ -362,7 +388,7 @@ __device__ __forceinline__ BlockMeta and_find_block(uint32_t& c_maxs, const uint
         bi = lo + lane;
         en = bi < nblocks ? __ldg(bd + bi) : make_uint2(0xffffffffu, 0u);
         hit = __ballot_sync(FULL, en.x >= bound) & ~1u;
-        DS2I_STAT(c_maxs += 32;)
+        DS2I_STAT(c.c_maxs += 32;)
     }
     const uint32_t f = __ffs(hit) - 1;
     BlockMeta r;
@@ -385,21 +411,22 @@ __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* d, uint32_t x
     return pos;
 }
 
-template <int CODEC, bool RANKED, int MIN_CTAS>
+template <int CODEC, bool RANKED, int MIN_CTAS, bool STATS = true>
 __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, DevWand wand, DevBatch batch, AndJob job, uint32_t k, int slots) {
     s16_table_init(smem_words(0));
     __syncthreads();
 
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    uint8_t* base = g_smem + S16_TAB_BYTES + warp * and_warp_smem_bytes(slots);
+    uint8_t* base = g_smem + S16_TAB_BYTES + warp * and_warp_smem_bytes(slots, CODEC == CODEC_PEF);
     AndWarp* ws = reinterpret_cast<AndWarp*>(base);
     AndList* st = reinterpret_cast<AndList*>(base + sizeof(AndWarp));
     uint32_t* ftmp = reinterpret_cast<uint32_t*>(base + sizeof(AndWarp) + size_t(slots) * sizeof(AndList));
     uint32_t* stage = ftmp + BLOCK;
     uint32_t* stack = stage + STAGE_WORDS;
 
-    AndCtx c;
+    AndCtxT<STATS> c;
+    c.fcache_off = smem_offset(stack + SCRATCH_WORDS);
     c.lists = idx.lists; c.stage = stage; c.bar = &ws->bar;
     c.stage_off = smem_offset(stage); c.stack_off = smem_offset(stack); c.ftmp_off = smem_offset(ftmp);
     c.phase = 0; c.win_slot = 0xffffffffu; c.win_delta = 0;
@@ -430,6 +457,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             const uint32_t src = batch.ord_size[t0 + lane];
             if (RANKED) ws->qw[lane] = batch.q_weight[t0 + src];
             and_list_setup<CODEC>(idx, &st[lane], batch.term[t0 + src]);
+            if (CODEC == CODEC_PEF) (reinterpret_cast<PefFreqSlot*>(g_smem + c.fcache_off) + lane)->fp = 0xffffffffu;
         }
         __syncwarp();
 
@@ -447,8 +475,64 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                 first_prev_max = en.x; first_prev_end = en.y;
             }
         }
+        uint32_t b_begin = first_block;
+        // ---- single-term queries (a tenth of a query log, but whole lists: a fifth of all driver blocks) ----
+        if (!RANKED && CODEC != CODEC_PEF && nt == 1) {
+            // and_query over one list counts its postings (queries.hpp:58-83 with an empty inner loop): nothing to decode
+            matches = min(st[0].n, b_end * BLOCK) - first_block * BLOCK;
+            b_begin = b_end;
+        }
+        if (RANKED && CODEC == CODEC_OPTPFOR && nt == 1) {
+            // ranked_and over one list is the top-k of qw * doc_term_weight(freq, norm_len[doc]) over its postings.  The freqs
+            // block is decoded FIRST: qw * doc_term_weight(freq, smallest norm_len of the collection) bounds the score of a
+            // posting from above (every fp32 step of bm25.hpp:11-15 is monotone), so once the heap is full a block none of
+            // whose postings can beat the threshold needs neither its docids nor the norm_len gathers.  Same top-k, bit for bit.
+            AndList* s = &st[0];
+            const float qw0 = ws->qw[0];
+            for (; b_begin < b_end; ++b_begin) {
+                const uint32_t b0 = b_begin, l = b0 - first_block;
+                if ((b0 + 1u) * BLOCK > s->n) break;                     // the partial last block: the general path below
+                const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
+                const uint32_t e0 = l ? pe : first_prev_end, e1 = __shfl_sync(FULL, m_end, l);
+                const uint32_t cur_base = (l ? pm : first_prev_max) + 1u, cur_max = __shfl_sync(FULL, m_max, l);
+                const uint32_t off = and_stage(c.lists, s->data_off + e0, s->data_off + e1, c.stage, c.bar, c.phase);
+                c.win_slot = 0xffffffffu;
+                const uint32_t w0 = lds_u32(stage, off);
+                const uint32_t docs_bytes = (w0 >> 26) >= 32u ? 4u * 129u : 4u * (1u + (w0 & 0xffffu) + 4u * (w0 >> 26));     // newpfor.h:204-209,254-286
+                bool prefix;
+                const uint32_t fbytes = and_decode_values<CODEC>(c.stage_off, off + docs_bytes, BLOCK, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
+                const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
+                const uint32_t f[4] = {fv.x + 1u, fv.y + 1u, fv.z + 1u, fv.w + 1u};
+                uint32_t pass = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pass |= uint32_t(topk.would_enter(qw0 * doc_term_weight(f[j], wand.min_norm_len))) << j;
+                DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += fbytes;)
+                if (!__any_sync(FULL, pass)) continue;
+                const uint32_t dbytes = and_decode_values<CODEC>(c.stage_off, off, BLOCK, cur_max - cur_base - (BLOCK - 1u), smem_offset(s->docs), c.stack_off, prefix);
+                uint4 v = reinterpret_cast<uint4*>(s->docs)[lane];
+                v.y += v.x; v.z += v.y; v.w += v.z;
+                const uint32_t incl = warp_inclusive_scan(v.w);
+                const uint32_t add = cur_base + (incl - v.w) + 4u * lane;     // docid_i = base + sum_{k<=i} gap_k + i
+                const uint32_t doc[4] = {v.x + add, v.y + add + 1u, v.z + add + 2u, v.w + add + 3u};
+                __syncwarp();
+                float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (pass & (1u << j)) sc[j] = qw0 * doc_term_weight(f[j], __ldg(wand.norm_lens + doc[j]));
+                DS2I_STAT(c.c_docs_blocks += 1; c.c_bytes_docs += dbytes; c.c_scored += __reduce_add_sync(FULL, __popc(pass));)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned want = __ballot_sync(FULL, (pass & (1u << j)) && topk.would_enter(sc[j]));
+                    while (want) {
+                        const int src = __ffs(want) - 1;
+                        want &= want - 1;
+                        topk.insert(__shfl_sync(FULL, sc[j], src), __shfl_sync(FULL, doc[j], src));
+                    }
+                }
+            }
+        }
         bool exhausted = false;
-        for (uint32_t b0 = first_block; b0 < b_end && !exhausted; ++b0) {
+        for (uint32_t b0 = b_begin; b0 < b_end && !exhausted; ++b0) {
             {
                 const uint32_t l = b0 - first_block;
                 const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
@@ -503,7 +587,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                     const uint32_t cur_block = s->cur_block;
                     if (cur_block == 0xffffffffu || cmin > s->cur_max) {
                         const bool fresh = cur_block == 0xffffffffu;
-                        const BlockMeta bm = and_find_block(c.c_maxs, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
+                        const BlockMeta bm = and_find_block(c, bd, s->nblocks, fresh ? 0u : cur_block + 1, fresh ? 0xffffffffu : s->cur_max,
                                                             fresh ? 0u : s->cur_end, cmin);
                         and_decode_docs<CODEC>(c, idx, s, i, bm.block, bm.e0, bm.e1, bm.prev_max, bm.cur_max);
                     }
@@ -607,7 +691,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         }
     }
 
-    if (batch.stats && lane == 0) {
+    if (STATS && batch.stats && lane == 0) {
         atomicAdd(&batch.stats[0], (unsigned long long)c.c_docs_blocks);
         atomicAdd(&batch.stats[1], (unsigned long long)c.c_freqs_blocks);
         atomicAdd(&batch.stats[2], (unsigned long long)c.c_bytes_docs);

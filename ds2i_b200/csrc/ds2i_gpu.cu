@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <cstdlib>
 #include <ctime>
 #include <memory>
@@ -397,6 +398,9 @@ extern "C" int ds2i_gpu_wand_open(const void* file_bytes, size_t nbytes, int dev
         if (f.num_docs) CUDA_TRY(cudaMemcpy(w->d_norm_lens.p, f.norm_lens, f.num_docs * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(w->d_max_term_weight.upload(w->h_max_term_weight));
         w->dev.norm_lens = w->d_norm_lens.p; w->dev.max_term_weight = w->d_max_term_weight.p;
+        float mn = f.num_docs ? std::numeric_limits<float>::max() : 0.f;
+        for (uint64_t i = 0; i < f.num_docs; ++i) { float v; memcpy(&v, f.norm_lens + 4 * i, 4); mn = std::min(mn, v); }
+        w->dev.min_norm_len = mn;
     } catch (std::exception const& e) {
         return fail(DS2I_E_FORMAT, e.what());
     }
@@ -728,7 +732,7 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     int grid = per_sm * ix->sm_count;
     int needed = int((b->nq + warps - 1) / warps);
     if (grid > needed) grid = std::max(needed, 1);
-    DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr};
+    DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr, 0.f};
     kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, k, b->max_terms);
     return DS2I_OK;
 }
@@ -737,17 +741,22 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
 #define DS2I_AND_MIN_CTAS 6
 #endif
 constexpr int AND_MIN_CTAS = DS2I_AND_MIN_CTAS;     // 6: 24 resident warps per SM (<= 80 registers per thread)
+// the Elias-Fano window decoders carry a wide partition descriptor (PefBody): fewer, fatter warps beat spilling it
+#ifndef DS2I_PEF_MIN_CTAS
+#define DS2I_PEF_MIN_CTAS 4
+#endif
+constexpr int and_min_ctas(int codec) { return codec == CODEC_PEF ? DS2I_PEF_MIN_CTAS : AND_MIN_CTAS; }
 
-template <int CODEC, bool RANKED, int MIN_CTAS = AND_MIN_CTAS>
+template <int CODEC, bool RANKED, bool STATS = true, int MIN_CTAS = and_min_ctas(CODEC)>
 static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    auto kern = and_block_kernel<CODEC, RANKED, MIN_CTAS>;
-    DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr};
+    auto kern = and_block_kernel<CODEC, RANKED, MIN_CTAS, STATS>;
+    DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr, 0.f};
     if (b->n_and_items) {
         int slots = b->max_terms;
         if (const char* ev = getenv("DS2I_GPU_SLOTS_OVERRIDE")) slots = std::max(slots, atoi(ev));     // occupancy experiments
-        size_t smem = S16_TAB_BYTES + warps * and_warp_smem_bytes(slots);
+        size_t smem = S16_TAB_BYTES + warps * and_warp_smem_bytes(slots, CODEC == CODEC_PEF);
         int per_sm = 0;
         int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
         if (orc != DS2I_OK) return orc;
@@ -770,10 +779,12 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
 
 // the conjunctive kernel is instantiated per codec: the path is issue-bound and a codec-specific
 // instance is a third smaller than one that dispatches at run time
+// (no_stats: the instance without the work counters, built for the benchmarked index types only — DS2I_RUN_NO_STATS)
 template <bool RANKED>
-static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
+static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k, bool no_stats) {
     switch (b->index->codec) {
         case CODEC_OPTPFOR:
+            if (no_stats) return launch_and_block<CODEC_OPTPFOR, RANKED, false>(b, db, k);
             return launch_and_block<CODEC_OPTPFOR, RANKED>(b, db, k);
 #ifndef DS2I_DEV_FAST_BUILD
         case CODEC_VARINT: return launch_and_block<CODEC_VARINT, RANKED>(b, db, k);
@@ -790,12 +801,12 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
 #endif
 constexpr int UNION_MIN_CTAS = DS2I_UNION_MIN_CTAS;
 
-template <int CODEC>
+template <int CODEC, bool STATS = true>
 static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    auto kern = union_drive_kernel<CODEC, UNION_MIN_CTAS>;
-    size_t smem = S16_TAB_BYTES + warps * union_warp_smem_bytes(b->max_terms);
+    auto kern = union_drive_kernel<CODEC, CODEC == CODEC_PEF ? DS2I_PEF_MIN_CTAS : UNION_MIN_CTAS, STATS>;
+    size_t smem = S16_TAB_BYTES + warps * union_warp_smem_bytes(b->max_terms, CODEC == CODEC_PEF);
     int per_sm = 0;
     int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
     if (orc != DS2I_OK) return orc;
@@ -854,18 +865,20 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     CUDA_TRY(cudaEventRecord(b->ev0));
     int rc = DS2I_OK;
     if (b->nq) {
-        const bool fast = !(flags & DS2I_RUN_FAITHFUL);
-        if (ix->kind == KIND_PEF && fast && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u))
-            rc = op == OP_AND ? launch_and_block<CODEC_PEF, false>(b, db, k) : launch_and_block<CODEC_PEF, true>(b, db, k);
+        const bool fast = !(flags & DS2I_RUN_FAITHFUL), no_stats = (flags & DS2I_RUN_NO_STATS) != 0;
+        if (ix->kind == KIND_PEF && fast && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
+            if (op == OP_AND) rc = launch_and_block<CODEC_PEF, false>(b, db, k);
+            else rc = no_stats ? launch_and_block<CODEC_PEF, true, false>(b, db, k) : launch_and_block<CODEC_PEF, true>(b, db, k);
+        }
         else if (ix->kind == KIND_PEF && fast && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u))
-            rc = launch_union_block<CODEC_PEF>(b, db, k);
-        else if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
+            rc = no_stats ? launch_union_block<CODEC_PEF, false>(b, db, k) : launch_union_block<CODEC_PEF>(b, db, k);
+        else if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr, 0.f}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
-            rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k) : launch_and_block_codec<true>(b, db, k);
+            rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k, no_stats) : launch_and_block_codec<true>(b, db, k, no_stats);
         }
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u)) {
             switch (ix->codec) {       // per-codec instances: smaller kernels, fewer instruction-cache misses
-                case CODEC_OPTPFOR: rc = launch_union_block<CODEC_OPTPFOR>(b, db, k); break;
+                case CODEC_OPTPFOR: rc = no_stats ? launch_union_block<CODEC_OPTPFOR, false>(b, db, k) : launch_union_block<CODEC_OPTPFOR>(b, db, k); break;
 #ifndef DS2I_DEV_FAST_BUILD
                 case CODEC_VARINT: rc = launch_union_block<CODEC_VARINT>(b, db, k); break;
                 case CODEC_INTERPOLATIVE: rc = launch_union_block<CODEC_INTERPOLATIVE>(b, db, k); break;

@@ -38,10 +38,13 @@ struct GlobalBits {
     __device__ __forceinline__ uint64_t word(uint64_t w) const { return __ldg(p + w); }
 };
 struct StagedBits {
-    const uint64_t* smem;
-    uint64_t w0;
+    uint32_t smem_off;      // byte offset of the window inside the kernel's dynamic shared memory (g_smem)
     uint32_t nw;
-    __device__ __forceinline__ uint64_t word(uint64_t w) const { const uint64_t i = w - w0; return i < nw ? smem[i] : 0ull; }
+    uint64_t w0;
+    __device__ __forceinline__ uint64_t word(uint64_t w) const {
+        const uint64_t i = w - w0;
+        return i < nw ? reinterpret_cast<const uint64_t*>(g_smem + smem_off)[i] : 0ull;
+    }
 };
 
 struct PefListDir {
@@ -88,13 +91,31 @@ __device__ __forceinline__ uint64_t bv_get_bits64(Bits const& bits, uint64_t pos
     return v & ((uint64_t(1) << len) - 1);
 }
 
-// k-th (0-based) set bit of a 64-bit word
+// k-th (0-based) set bit of a 64-bit word: popcount bisection (the __fns intrinsic is a software loop — it was a quarter of
+// all instructions of the window decoder)
 __device__ __forceinline__ uint32_t select_in_word(uint64_t w, uint32_t k) {
-    uint32_t lo = uint32_t(w), hi = uint32_t(w >> 32);
-    uint32_t pl = __popc(lo);
-    if (k < pl) return __fns(lo, 0, int(k) + 1);
-    return 32u + __fns(hi, 0, int(k - pl) + 1);
+    uint32_t x = uint32_t(w), r = 0;
+    const uint32_t pl = __popc(x);
+    if (k >= pl) { k -= pl; x = uint32_t(w >> 32); r = 32; }
+#pragma unroll
+    for (uint32_t s = 16; s >= 1; s >>= 1) {
+        const uint32_t c = __popc(x & ((1u << s) - 1u));
+        if (k >= c) { k -= c; x >>= s; r += s; }
+    }
+    return r;
 }
+
+// either of the two, chosen at run time (warp-uniformly): ONE instance of the de-inlined window decoder serves both
+struct AnyBits {
+    const uint64_t* p;
+    uint64_t w0;
+    uint32_t smem_off;
+    uint32_t nw;            // 0: read HBM
+    __device__ __forceinline__ uint64_t word(uint64_t w) const {
+        if (nw) { const uint64_t i = w - w0; return i < nw ? reinterpret_cast<const uint64_t*>(g_smem + smem_off)[i] : 0ull; }
+        return __ldg(p + w);
+    }
+};
 
 // Layout of one partition body, resolved from (universe, n) like the reference constructors do.
 struct PefBody {
@@ -110,8 +131,9 @@ struct PefBody {
 };
 
 // indexed_sequence / strict_sequence dispatch (indexed_sequence.hpp:95-127, strict_sequence.hpp:104-137)
-template <class Bits>
-__device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, Bits const& bits, PefPart const& p, bool strict) {
+// known_type: the partition's type bit when the caller has it cached (0xffffffff: read it from the body)
+template <class Seq, class Bits>
+__device__ __forceinline__ PefBody pef_open_body(Seq const& seq, Bits const& bits, PefPart const& p, bool strict, uint32_t known_type = 0xffffffffu) {
     PefBody b;
     b.n = p.size;
     b.universe = p.ub - p.base + 1u;            // last relative value + 1
@@ -120,7 +142,7 @@ __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, Bits const& 
     if (seq.raw_ef) b.type = PEF_EF;            // compact_elias_fano.hpp:63-136 / strict_elias_fano.hpp:20-36 written directly
     else {
         if (b.universe == b.n) { b.type = PEF_AO; return b; }
-        b.type = uint32_t(bits.word(p.bit_off >> 6) >> (p.bit_off & 63)) & 1u;
+        b.type = known_type != 0xffffffffu ? known_type : uint32_t(bits.word(p.bit_off >> 6) >> (p.bit_off & 63)) & 1u;
         off += 1;
     }
     if (b.type == PEF_EF) {
@@ -130,7 +152,8 @@ __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, Bits const& 
         b.log_s1 = seq.log_sampling1;
         uint64_t u = strict ? uint64_t(b.universe) - b.n + 1 : uint64_t(b.universe);
         uint64_t n = b.n;
-        b.lower_bits = u > n ? 63u - uint32_t(__clzll(u / n)) : 0u;
+        // msb(u / n): a 32-bit division whenever both fit (the 64-bit one is an ~80-instruction routine)
+        b.lower_bits = u > n ? ((u >> 32) ? 63u - uint32_t(__clzll(u / n)) : 31u - uint32_t(__clz(uint32_t(u) / uint32_t(n)))) : 0u;
         uint64_t hbl = n + (u >> b.lower_bits) + 2;
         b.pointer_size = ceil_log2_dev(hbl);
         uint64_t p0 = b.log_s0 >= 63 ? 0 : ((hbl - n) >> b.log_s0);
@@ -154,13 +177,15 @@ __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, Bits const& 
 }
 
 // Positions (relative to `origin`) of the set bits with ordinals r0 .. r0+cnt-1 (ordinal 0 = first
-// set bit at or after `start`), cnt <= 128, written to out[0..cnt).  32 words per step.
+// set bit at or after `start`), cnt <= 129: the first 128 go to out[0..), the 129th (the freqs path decodes one element
+// before its window) is returned, warp-uniformly.  32 words per step.
 template <class Bits>
-__device__ __forceinline__ void pef_scan_ones(Bits const& bits, uint64_t start, uint64_t origin, uint32_t r0, uint32_t cnt, uint32_t* out) {
+__device__ __forceinline__ uint32_t pef_scan_ones(Bits const& bits, uint64_t start, uint64_t origin, uint32_t r0, uint32_t cnt, uint32_t* out) {
     const unsigned lane = lane_id();
     uint64_t wbase = start >> 6;
     uint32_t seen = 0;                    // set bits before the words of this step
     const uint32_t r1 = r0 + cnt;
+    uint32_t extra = 0;
     bool first = true;
     while (seen < r1) {
         uint64_t w = bits.word(wbase + lane);
@@ -170,32 +195,35 @@ __device__ __forceinline__ void pef_scan_ones(Bits const& bits, uint64_t start, 
         uint32_t incl = warp_inclusive_scan(pc);
         uint32_t excl = seen + incl - pc;
         uint32_t total = seen + __shfl_sync(FULL, incl, 31);
-        // every lane looks for "its" outputs among the words of this step
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint32_t o = r0 + lane + 32u * j;            // ordinal wanted
-            bool want = (lane + 32u * j) < cnt && o >= seen && o < total;
-            uint32_t t = 0;                               // word holding ordinal o: largest t with excl_t <= o
+        // the word holding ordinal o: largest t with excl_t <= o.  (Words with no set bits share excl with their successor;
+        // the search prefers the later one, which is the one that owns the ordinal.)
+        auto locate = [&](uint32_t o, bool want, uint32_t& pos) {
+            uint32_t t = 0;
 #pragma unroll
             for (uint32_t s = 16; s >= 1; s >>= 1) {
                 uint32_t e = __shfl_sync(FULL, excl, (t + s) & 31u);
                 if (e <= o) t += s;
             }
-            // words with no set bits share excl with their successor; the search lands on the last such
-            // word, which is the one that owns the ordinal when it has bits — walk back is not needed
-            // because an empty word's excl equals the next word's excl and the search prefers the later one.
             uint32_t we = __shfl_sync(FULL, excl, t);
             uint32_t wlo = __shfl_sync(FULL, uint32_t(w), t), whi = __shfl_sync(FULL, uint32_t(w >> 32), t);
-            if (want) {
-                uint64_t ww = (uint64_t(whi) << 32) | wlo;
-                uint32_t bit = select_in_word(ww, o - we);
-                out[lane + 32u * j] = uint32_t((wbase + t) * 64 + bit - origin);
-            }
+            if (want) pos = uint32_t((wbase + t) * 64 + select_in_word((uint64_t(whi) << 32) | wlo, o - we) - origin);
+            return want;
+        };
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t o = r0 + lane + 32u * j;            // ordinal wanted
+            uint32_t pos = 0;
+            if (locate(o, (lane + 32u * j) < cnt && o >= seen && o < total, pos)) out[lane + 32u * j] = pos;
+        }
+        if (cnt > 128u) {                                       // warp-uniform
+            const uint32_t o = r0 + 128u;
+            locate(o, o >= seen && o < total, extra);
         }
         seen = total;
         wbase += 32;
     }
     __syncwarp();
+    return extra;
 }
 
 // count of ZERO bits wanted: position (relative to origin) of the zero with ordinal z (0 = first zero
@@ -226,9 +254,11 @@ __device__ __forceinline__ uint64_t pef_select_zero(Bits const& bits, uint64_t s
     }
 }
 
-// Elements [i0, i0+cnt) of a partition (cnt <= 128) as ABSOLUTE values (base added) into out[0..cnt).
+// Elements [i0, i0+cnt) of a partition (cnt <= 128) as ABSOLUTE values (base added) into out[0..cnt).  with_prev (i0 > 0):
+// element i0 - 1 is decoded along (one scan instead of two) and returned, warp-uniformly; otherwise 0 is returned.
 template <class Bits>
-__device__ __forceinline__ void pef_decode_range(Bits const& bits, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out) {
+__device__ __forceinline__ uint32_t pef_decode_range(Bits const& bits, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out,
+                                                     bool with_prev = false) {
     const unsigned lane = lane_id();
     if (b.type == PEF_AO) {
 #pragma unroll
@@ -237,46 +267,49 @@ __device__ __forceinline__ void pef_decode_range(Bits const& bits, PefPart const
             if (e < cnt) out[e] = p.base + i0 + e;
         }
         __syncwarp();
-        return;
+        return with_prev ? p.base + i0 - 1u : 0u;
     }
-    const uint32_t s = i0 >> b.log_s1;                     // pointers1 sample at or before i0
-    if (b.type == PEF_EF) {
-        uint64_t start = b.high_off;
-        uint32_t r0 = i0;
-        if (s) {
-            uint64_t ptr = bv_get_bits64(bits, b.pointers1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
-            start = b.high_off + ptr;                      // high-bit position of element s << log_s1
-            r0 = i0 - (s << b.log_s1);
-        }
-        pef_scan_ones(bits, start, b.high_off, r0, cnt, out);
+    const uint32_t shift = with_prev ? 1u : 0u;
+    const uint32_t f0 = i0 - shift, total = cnt + shift;   // decoded elements: [f0, f0 + total), total <= 129
+    const uint32_t s = f0 >> b.log_s1;                     // pointers1 sample at or before f0
+    const bool ef = b.type == PEF_EF;
+    uint64_t origin = ef ? b.high_off : b.bitmap_off;
+    uint64_t start = origin;
+    uint32_t r0 = f0;
+    if (s) {
+        // EF: high-bit position of element s << log_s1; bitvector: its value = its bit position
+        uint64_t ptr = bv_get_bits64(bits, (ef ? b.pointers1_off : b.rb_ptr1_off) + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
+        start = origin + ptr;
+        r0 = f0 - (s << b.log_s1);
+    }
+    const uint32_t extra = pef_scan_ones(bits, start, origin, r0, total, out);
+    // positions -> values; with_prev moves every value one slot down (element f0 goes to the return register), so all
+    // positions are read before any value is written
+    uint32_t pos[4];
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint32_t e = lane + 32u * j;
-            if (e < cnt) {
-                uint32_t i = i0 + e;
-                uint32_t high = out[e] - i - 1u;
-                uint32_t low = bv_get_bits(bits, b.low_off + uint64_t(i) * b.lower_bits, b.lower_bits);
-                uint32_t v = (high << b.lower_bits) | low;
-                if (b.strict) v += i;                      // strict_elias_fano.hpp:50-60
-                out[e] = p.base + v;
-            }
-        }
-    } else {
-        uint64_t start = b.bitmap_off;
-        uint32_t r0 = i0;
-        if (s) {
-            uint64_t ptr = bv_get_bits64(bits, b.rb_ptr1_off + uint64_t(s - 1) * b.pointer_size, b.pointer_size);
-            start = b.bitmap_off + ptr;                    // value of element s << log_s1 = its bit position
-            r0 = i0 - (s << b.log_s1);
-        }
-        pef_scan_ones(bits, start, b.bitmap_off, r0, cnt, out);
+    for (uint32_t j = 0; j < 4; ++j) { const uint32_t e = lane + 32u * j; pos[j] = e < total ? out[e] : 0u; }
+    if (with_prev) __syncwarp();
+    auto value = [&](uint32_t e, uint32_t ps) {
+        if (!ef) return p.base + ps;
+        const uint32_t i = f0 + e;
+        const uint32_t high = ps - i - 1u;
+        const uint32_t low = bv_get_bits(bits, b.low_off + uint64_t(i) * b.lower_bits, b.lower_bits);
+        uint32_t v = (high << b.lower_bits) | low;
+        if (b.strict) v += i;                              // strict_elias_fano.hpp:50-60
+        return p.base + v;
+    };
+    uint32_t prev = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint32_t e = lane + 32u * j;
-            if (e < cnt) out[e] = p.base + out[e];
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t e = lane + 32u * j;
+        if (e < total && e < 128u) {
+            const uint32_t v = value(e, pos[j]);
+            if (e >= shift) out[e - shift] = v; else prev = v;
         }
     }
+    if (total > 128u && lane == 0) out[127] = value(128u, extra);
     __syncwarp();
+    return with_prev ? __shfl_sync(FULL, prev, 0) : 0u;
 }
 
 // Index of the first element whose high part is >= (x >> l) (EF) / whose value is >= x (bitvector,
@@ -325,10 +358,28 @@ __device__ __forceinline__ uint32_t pef_rank_hint(Bits const& bits, PefBody cons
     return rank + __reduce_add_sync(FULL, acc);
 }
 
+// what pef_open_body needs of a PefSeq, by value (argument of the de-inlined window decoder)
+struct PefSeqParams {
+    uint32_t log_sampling0, log_sampling1, rb_log_rank1_sampling, rb_log_sampling1, raw_ef;
+};
+__device__ __forceinline__ PefSeqParams pef_params(PefSeq const& s) {
+    return PefSeqParams{s.log_sampling0, s.log_sampling1, s.rb_log_rank1_sampling, s.rb_log_sampling1, s.raw_ef};
+}
+
+// Elements [i0, i0 + cnt) of partition p (cnt <= 128) as absolute values into the shared-memory words at out_off.  De-inlined:
+// the block-parallel query kernels decode windows at several call sites (driving list, probed lists, docs and freqs), and one
+// inlined copy per site (~2.5 k instructions each) made them fetch-bound — 34 issue slots lost to instruction misses per issue.
+// with_prev: also returns element i0 - 1 (i0 > 0).
+__device__ __noinline__ uint32_t pef_window_values(PefSeqParams seq, AnyBits bits, PefPart p, bool strict, uint32_t i0, uint32_t cnt, uint32_t out_off,
+                                                   bool with_prev, uint32_t known_type = 0xffffffffu) {
+    const PefBody b = pef_open_body(seq, bits, p, strict, known_type);
+    return pef_decode_range(bits, p, b, i0, cnt, smem_words(out_off), with_prev);
+}
+
 // the same straight from HBM (what the literal enumerator and the full-decode kernels use)
 __device__ __forceinline__ PefBody pef_open_body(PefSeq const& seq, PefPart const& p, bool strict) { return pef_open_body(seq, GlobalBits{seq.bits}, p, strict); }
 __device__ __forceinline__ void pef_decode_range(PefSeq const& seq, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out) {
-    pef_decode_range(GlobalBits{seq.bits}, p, b, i0, cnt, out);
+    pef_decode_range(GlobalBits{seq.bits}, p, b, i0, cnt, out, false);
 }
 __device__ __forceinline__ uint32_t pef_rank_hint(PefSeq const& seq, PefBody const& b, uint32_t x) { return pef_rank_hint(GlobalBits{seq.bits}, b, x); }
 

@@ -3,6 +3,8 @@
 // semantics (freq_index.hpp:116-190, partitioned_sequence.hpp:122-347, positive_sequence.hpp:33-78),
 // and the kernels behind decode_lists / next_geq_batch / the query operators for this index type.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -541,6 +543,15 @@ struct PefIndexHost {
             device_bytes = docs.device_bytes + freqs.device_bytes;
             rc = build_block_directory(err);
             if (rc) return rc;
+            if (getenv("DS2I_GPU_TRACE")) {
+                uint64_t staged = 0, big_windows = 0;
+                for (auto const& pp : docs.parts) {
+                    const uint64_t bytes = ((pp.bit_off + pp.body_bits + 7) >> 3) - (pp.bit_off >> 3) + 30;
+                    if (pp.body_bits && bytes <= 1280) ++staged; else big_windows += (uint64_t(pp.size) + 127) / 128;
+                }
+                fprintf(stderr, "[ds2i_gpu] opt index: %llu lists, %zu docs partitions (%llu small enough to stage; %llu windows in the others), %zu freqs partitions, %llu windows\n",
+                        (unsigned long long)size, docs.parts.size(), (unsigned long long)staged, (unsigned long long)big_windows, freqs.parts.size(), (unsigned long long)total_blocks);
+            }
         } catch (std::exception const& e) {
             err = e.what();
             return -2;

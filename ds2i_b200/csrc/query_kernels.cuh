@@ -16,6 +16,7 @@ enum : int { OP_AND = 0, OP_AND_FREQ = 1, OP_OR = 2, OP_OR_FREQ = 3, OP_RANKED_A
 struct DevWand {
     const float* norm_lens;         // wand_data::norm_len   (wand_data.hpp:55-58)
     const float* max_term_weight;   // wand_data::max_term_weight (:60-63)
+    float min_norm_len;             // smallest norm_len of the collection: bm25::doc_term_weight(f, .) is largest there
 };
 
 struct DevBatch {

@@ -116,6 +116,10 @@ int ds2i_gpu_batch_run(ds2i_gpu_batch*, int op, uint32_t k, float* out_elapsed_m
  * caller may enqueue a collective or a copy behind it, or call ds2i_gpu_batch_wait (which also reports the CUDA-event time).
  * The fetch / stats calls copy on the same stream and therefore see the finished results either way. */
 #define DS2I_RUN_ASYNC 2u
+/* DS2I_RUN_NO_STATS: run the kernel instance without the algorithmic-work counters of ds2i_gpu_batch_stats (they then read 0).
+ * The counters cost registers in register-bound kernels; a benchmark times launches without them and collects them from one
+ * more launch of the same batch.  Instances exist for block_optpfor and the Elias-Fano family; other types ignore the flag. */
+#define DS2I_RUN_NO_STATS 4u
 int ds2i_gpu_batch_run_ex(ds2i_gpu_batch*, int op, uint32_t k, uint32_t flags, float* out_elapsed_ms);
 int ds2i_gpu_batch_wait(ds2i_gpu_batch*, float* out_elapsed_ms);
 int ds2i_gpu_batch_fetch(ds2i_gpu_batch*, uint64_t* out_counts, float* out_scores);   /* D2H of the last run */

@@ -21,15 +21,16 @@ def child(args):
     import bench
     import ds2i_b200 as d
     a = argparse.Namespace(docs=args.docs, terms=args.terms, seed=20261017, queries=args.queries, queries_total=80000)
-    paths = bench.ensure_data(a)
-    index = d.Index(paths["index"], "block_optpfor", 0)
+    paths = bench.ensure_data(a, 0, (args.itype,))
+    index = d.Index(paths[args.itype], args.itype, 0)
     wdata = d.WandData(paths["wand"], 0)
     queries = d.read_queries(paths["queries"], args.queries)
     batch = d.QueryBatch(index, wdata, queries)
     for op in args.ops.split(","):
         for _ in range(3):
-            batch.run(op, 10)
-        ms = [batch.run(op, 10) for _ in range(args.steps)]
+            batch.run(op, 10, stats=not args.no_stats)
+        ms = [batch.run(op, 10, stats=not args.no_stats) for _ in range(args.steps)]
+        batch.run(op, 10)
         st = batch.stats()
         counts, scores = batch.fetch()
         h = hashlib.sha1(counts.tobytes() + (scores.tobytes() if op in d.RANKED else b"")).hexdigest()[:16]
@@ -47,6 +48,8 @@ def main():
     ap.add_argument("--terms", type=int, default=1_000_000)
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--itype", default="block_optpfor")
+    ap.add_argument("--no-stats", action="store_true", help="time the kernel instances without the work counters (DS2I_RUN_NO_STATS)")
     ap.add_argument("libs", nargs="*")
     args = ap.parse_args()
     if args.child:
@@ -57,7 +60,7 @@ def main():
         if lib:
             env["DS2I_GPU_LIB"] = os.path.abspath(lib)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--ops", args.ops, "--steps", str(args.steps), "--docs", str(args.docs),
-                            "--terms", str(args.terms), "--queries", str(args.queries)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                            "--terms", str(args.terms), "--queries", str(args.queries), "--itype", args.itype] + (["--no-stats"] if args.no_stats else []), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         sys.stderr.write(r.stderr[-4000:])
         if r.returncode != 0:
             print(json.dumps({"lib": lib, "failed": r.stderr[-600:]}), flush=True)
