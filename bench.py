@@ -367,19 +367,35 @@ def main():
         """W warm-up + K timed steps of `op` over the resident batch, then the end-to-end leg."""
         batch = d.QueryBatch(idx, wdata, queries)
         pad = max(shard_sizes) * (8 + 8 * args.k) if op in d.RANKED else max(shard_sizes) * 8
-        gathered = torch.empty((world, pad), dtype=torch.uint8, device="cuda") if world > 1 else None
+        # the gather of step t overlaps the kernels of step t + 1: the fused results are copied (device to device, on the kernels'
+        # stream) into one of two send buffers and all-gathered from there asynchronously on NCCL's stream
+        send = [torch.empty((pad,), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+        gathered = [torch.empty((world, pad), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+        pending = [None, None]
+        nstep = [0]
 
         def step():
             # the timed launches run the kernel instances WITHOUT the algorithmic-work counters (DS2I_RUN_NO_STATS: they cost
             # registers in register-bound kernels); one more launch of the same batch, below, collects them
             if world == 1:
                 return batch.run(op, args.k, stats=False)     # synchronises; returns the CUDA-event kernel time
-            batch.run(op, args.k, wait=False, stats=False)    # no host synchronisation inside a step:
-            gather_fused(batch.device_fused(pad_to=pad), world, gathered)      # the one collective is enqueued behind the kernels
+            batch.run(op, args.k, wait=False, stats=False)    # no host synchronisation inside a step
+            j = nstep[0] & 1
+            nstep[0] += 1
+            if pending[j] is not None:
+                pending[j].wait()                             # stream-level: the gather that last used this buffer pair (two steps ago)
+            send[j].copy_(batch.device_fused(pad_to=pad), non_blocking=True)
+            pending[j] = dist.all_gather_into_tensor(gathered[j], send[j], async_op=True)      # the ONE collective of the step
             return None
+
+        def drain():
+            for h in pending:
+                if h is not None:
+                    h.wait()
 
         for _ in range(args.warmup):
             step()
+        drain()
         barrier()
         launches0 = batch.stats()["launches"]
         kernel_ms = []
@@ -389,6 +405,7 @@ def main():
             ev0.record()
             for _ in range(args.steps):
                 kernel_ms.append(step())
+            drain()                                            # every gather of the timed steps has completed before the clock stops
             ev1.record()
             barrier()
         total_ms = ev0.elapsed_time(ev1)
@@ -405,7 +422,7 @@ def main():
         gathered_ok = None
         if world > 1:
             # the gathered buffer of the last step holds every shard's rows: check this rank's own slice
-            mine = gathered[rank].cpu().numpy()
+            mine = gathered[(nstep[0] - 1) & 1][rank].cpu().numpy()
             gc, gs, _ = split_fused(mine, len(queries), args.k) if op in d.RANKED else (mine[:len(queries) * 8].view(np.uint64), None, None)
             gathered_ok = bool(np.array_equal(gc, counts) and (gs is None or np.allclose(gs, scores, rtol=1e-5, atol=0)))
 

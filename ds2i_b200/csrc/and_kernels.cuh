@@ -40,6 +40,16 @@ __device__ __forceinline__ uint32_t hist_bucket(uint32_t n) { return n ? 31u - _
 
 constexpr uint32_t AND_CHUNK_BLOCKS = 32;     // blocks of the shortest list per work item
 
+// Double-buffered TMA for the driving list (its next block pair is copied into a second staging window while the current
+// block is probed).  Built and measured on B200 in round 2 (-DDS2I_DRIVER_PREFETCH=1): results identical, ranked_and 16.2 ->
+// 18.3 ms, and 9.0 -> 9.1 ms per 10k-query batch — the kernels are issue- and register-bound, not latency-bound (the copy's
+// latency was already covered by the other resident warps), and the extra state costs spills.  Off by default.
+#ifndef DS2I_DRIVER_PREFETCH
+#define DS2I_DRIVER_PREFETCH 0
+#endif
+constexpr bool AND_DRIVER_PREFETCH = DS2I_DRIVER_PREFETCH != 0;
+constexpr uint32_t AND_STAGE_WINDOWS = AND_DRIVER_PREFETCH ? 2 : 1;
+
 // Work items are implicit: query sched[p] owns ceil(blocks of its shortest list / chunk_blocks) consecutive items; a warp
 // maps a global item number to its query with a 32-ary search of the prefix array gstart (in processing order).
 struct AndJob {
@@ -90,8 +100,8 @@ static_assert(sizeof(AndList) == 48 + 4 * BLOCK, "AndList layout");
 
 struct AndWarp {
     float qw[MAX_TERMS];
-    uint64_t bar;
-    uint64_t pad;
+    uint64_t bar;           // mbarrier of the probe staging window
+    uint64_t dbar;          // mbarrier of the driving list's staging window (the next block pair is in flight while this one is probed)
 };
 
 // Elias-Fano path: the partition of the freqs sequence a list's last freqs window came from (lists are walked forward and
@@ -103,10 +113,11 @@ struct PefFreqSlot {
     uint32_t pad[6];
 };
 static_assert(sizeof(PefFreqSlot) == 64, "PefFreqSlot layout");
+constexpr uint32_t PEF_SCAN_SCRATCH_BYTES = 384;      // pef_scan_ones_smem: the words of a step and their first ordinals
 
 __host__ __device__ constexpr size_t and_warp_smem_bytes(int slots, bool pef = false) {
-    return sizeof(AndWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 +
-           (pef ? size_t(slots) * sizeof(PefFreqSlot) : 0);
+    return sizeof(AndWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + AND_STAGE_WINDOWS * STAGE_WORDS * 4 /* probe (+ driver) window */ +
+           SCRATCH_WORDS * 4 + (pef ? size_t(slots) * sizeof(PefFreqSlot) + PEF_SCAN_SCRATCH_BYTES : 0);
 }
 
 // staging window <- bytes [start, end) of m_lists (the enclosing 16-B aligned range, one TMA bulk copy,
@@ -175,7 +186,13 @@ struct AndCtxT {            // warp-uniform registers
     uint32_t* stage;
     uint64_t* bar;
     uint32_t stage_off, stack_off, ftmp_off;
-    uint32_t fcache_off;    // Elias-Fano path: the warp's PefFreqSlot array
+    uint32_t fcache_off;    // Elias-Fano path: the warp's scan scratch (PEF_SCAN_SCRATCH_BYTES), then its PefFreqSlot array
+    // double-buffered TMA: the driving list has its own staging window (right behind the probe window) and mbarrier (right
+    // behind bar); block pair b + 1 is copied while block b is probed against the other lists
+    uint32_t drv_slot;      // slot of the driving list
+    uint32_t dwin_block;    // driver block whose pair is (or is being copied) in the driver window; 0xffffffff: none
+    uint32_t dwin_delta;    // window offset of the list's data byte 0 (mod 2^32)
+    uint32_t dphase;        // bit 0: phase of dbar; bit 1: the copy in flight has not been waited for yet
     uint32_t phase;
     uint32_t win_slot;      // list slot whose current block pair sits in the staging window (0xffffffff: none)
     uint32_t win_delta;     // window offset of that list's data byte 0 (mod 2^32)
@@ -193,7 +210,8 @@ typedef AndCtxT<true> AndCtx;
 struct PefDocsWindow { uint32_t phase, staged_part, first_pos, cnt; };
 
 __device__ __noinline__ PefDocsWindow pef_window_docs(PefSeq seq, uint64_t first_part, uint32_t b, uint32_t part_rel, uint32_t stage_off, uint32_t bar_off,
-                                                      uint32_t phase, uint32_t staged_part /* partition in the staging window, 0xffffffff: none */, uint32_t docs_off) {
+                                                      uint32_t phase, uint32_t staged_part /* partition in the staging window, 0xffffffff: none */, uint32_t docs_off,
+                                                      uint32_t scratch_off) {
     const unsigned lane = lane_id();
     const PefPart p = pef_load_part(seq.parts, first_part + part_rel);
     const uint32_t i0 = (b - p.first_block) * BLOCK;
@@ -215,7 +233,7 @@ __device__ __noinline__ PefDocsWindow pef_window_docs(PefSeq seq, uint64_t first
         }
         bits.w0 = byte0 >> 3; bits.smem_off = stage_off; bits.nw = uint32_t((byte1 - byte0) >> 3);
     }
-    pef_window_values(pef_params(seq), bits, p, false, i0, cnt, docs_off, false);
+    pef_window_values(pef_params(seq), bits, p, false, i0, cnt, docs_off, false, scratch_off);
     uint32_t* docs = smem_words(docs_off);
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) { const uint32_t e = lane + 32u * j; if (e >= cnt) docs[e] = 0xffffffffu; }
@@ -226,7 +244,7 @@ __device__ __noinline__ PefDocsWindow pef_window_docs(PefSeq seq, uint64_t first
 // freq() - 1 of the postings at list positions [g0, g0 + cnt) -> the 128-word buffer at out_off.  positive_sequence over the strict
 // prefix sums c[] (positive_sequence.hpp:48-66): freq(i) = c[i] - c[i-1].  The freqs sequence has its own partitions; a docs
 // window may straddle two of them, so the range is decoded partition by partition.
-__device__ __noinline__ void pef_window_freqs(PefSeq seq, uint32_t term, uint32_t g0, uint32_t cnt, uint32_t fcache_slot_off, uint32_t out_off) {
+__device__ __noinline__ void pef_window_freqs(PefSeq seq, uint32_t term, uint32_t g0, uint32_t cnt, uint32_t fcache_slot_off, uint32_t out_off, uint32_t scratch_off) {
     const unsigned lane = lane_id();
     uint32_t* out = smem_words(out_off);
     const AnyBits gb{seq.bits, 0, 0, 0};
@@ -267,7 +285,7 @@ __device__ __noinline__ void pef_window_freqs(PefSeq seq, uint32_t term, uint32_
         // c[g0 - 1]: the value before a partition's first element is the previous partition's last value = base - 1
         // (partition 0: the sum before the first element is 0); otherwise the element before the window is decoded along
         const bool need_prev = !have_prev && local != 0;
-        const uint32_t pv = pef_window_values(pef_params(seq), gb, p, true, local, take, out_off + 4u * (g - g0), need_prev, type);
+        const uint32_t pv = pef_window_values(pef_params(seq), gb, p, true, local, take, out_off + 4u * (g - g0), need_prev, scratch_off, type);
         if (!have_prev) { prev = local ? pv : (fp ? p.base - 1u : 0u); have_prev = true; }
         g += take; ++fp;
         cached = false;
@@ -284,6 +302,34 @@ __device__ __noinline__ void pef_window_freqs(PefSeq seq, uint32_t term, uint32_
     __syncwarp();
 }
 
+// Start the copy of the driving list's block pair [e0, e1) (block b) into the driver window.  The window must not be read any
+// more (the caller has decoded what it needs of the previous pair).
+template <class List, class Ctx>
+__device__ __forceinline__ void and_prefetch_driver(Ctx& c, const List* s, uint32_t b, uint32_t e0, uint32_t e1) {
+    const uint64_t start = s->data_off + e0, end = s->data_off + e1;
+    const uint64_t a0 = start & ~uint64_t(15);
+    uint32_t bytes = uint32_t(((end + 15) & ~uint64_t(15)) - a0);
+    if (bytes > STAGE_BYTES) bytes = STAGE_BYTES;
+    __syncwarp();   // every lane is done reading the previous pair
+    c.dwin_block = b; c.dwin_delta = uint32_t(start - a0) - e0;
+    if (bytes) {
+        if (lane_id() == 0) {
+            uint64_t* dbar = c.bar + 1;
+            mbar_expect_tx(dbar, bytes);
+            tma_load_1d(c.stage + STAGE_WORDS, c.lists + a0, bytes, dbar);
+        }
+        c.dphase |= 2u;
+    }
+}
+// the copy started by and_prefetch_driver has landed (waits once per copy)
+template <class Ctx>
+__device__ __forceinline__ void and_driver_ready(Ctx& c) {
+    if (c.dphase & 2u) {
+        mbar_wait(c.bar + 1, c.dphase & 1u);
+        c.dphase = (c.dphase & 1u) ^ 1u;
+    }
+}
+
 // block_posting_list.hpp:292-319 with the block's metadata in hand: [e0, e1) = byte range of the block
 // pair inside the list's data, prev_max = block_max[b-1] (0xffffffff for b == 0), cur_max = block_max[b]
 template <int CODEC, class List, class Ctx>
@@ -291,7 +337,7 @@ __device__ __forceinline__ void and_decode_docs(Ctx& c, DevIndex const& idx, Lis
     if constexpr (CODEC == CODEC_PEF) {
         (void)e0; (void)prev_max;
         const PefDocsWindow w = pef_window_docs(idx.pdocs, s->data_off, b, e1, c.stage_off, smem_offset(c.bar), c.phase,
-                                                c.win_slot == slot ? c.win_delta : 0xffffffffu, smem_offset(s->docs));
+                                                c.win_slot == slot ? c.win_delta : 0xffffffffu, smem_offset(s->docs), c.fcache_off);
         c.phase = w.phase;
         if (w.staged_part != 0xffffffffu) { c.win_slot = slot; c.win_delta = w.staged_part; }
         // cur_end: the window's partition; freqs_off: list position of the window's first element; pad1: its size
@@ -305,9 +351,12 @@ __device__ __forceinline__ void and_decode_docs(Ctx& c, DevIndex const& idx, Lis
     const uint32_t cur_base = prev_max + 1u;
     const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
     const uint64_t data_off = s->data_off;
-    const uint32_t off = and_stage(c.lists, data_off + e0, data_off + e1, c.stage, c.bar, c.phase);
+    const bool in_dwin = slot == c.drv_slot && c.dwin_block == b;           // the pair was prefetched into the driver window
+    uint32_t off, win_off;
+    if (in_dwin) { and_driver_ready(c); off = e0 + c.dwin_delta; win_off = c.stage_off + STAGE_WORDS * 4u; }
+    else { off = and_stage(c.lists, data_off + e0, data_off + e1, c.stage, c.bar, c.phase); win_off = c.stage_off; }
     bool prefix;
-    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, off, size, cur_max - cur_base - (size - 1u), smem_offset(s->docs), c.stack_off, prefix);
+    const uint32_t consumed = and_decode_values<CODEC>(win_off, off, size, cur_max - cur_base - (size - 1u), smem_offset(s->docs), c.stack_off, prefix);
     if (prefix) {
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
@@ -324,7 +373,7 @@ __device__ __forceinline__ void and_decode_docs(Ctx& c, DevIndex const& idx, Lis
     }
     if (lane == 0) *reinterpret_cast<uint4*>(&s->cur_block) = make_uint4(b, cur_max, e1, e0 + consumed);
     __syncwarp();
-    c.win_slot = slot; c.win_delta = off - e0;
+    if (!in_dwin) { c.win_slot = slot; c.win_delta = off - e0; }
     DS2I_STAT(c.c_docs_blocks += 1; c.c_bytes_docs += consumed;)
 }
 
@@ -334,20 +383,22 @@ __device__ __forceinline__ void and_decode_docs(Ctx& c, DevIndex const& idx, Lis
 template <int CODEC, class List, class Ctx>
 __device__ __forceinline__ bool and_decode_freqs(Ctx& c, DevIndex const& idx, const List* s, uint32_t slot, uint32_t out_off) {
     if constexpr (CODEC == CODEC_PEF) {
-        pef_window_freqs(idx.pfreqs, s->term, s->freqs_off, s->pad1, c.fcache_off + slot * uint32_t(sizeof(PefFreqSlot)), out_off);
+        pef_window_freqs(idx.pfreqs, s->term, s->freqs_off, s->pad1, c.fcache_off + PEF_SCAN_SCRATCH_BYTES + slot * uint32_t(sizeof(PefFreqSlot)), out_off, c.fcache_off);
         DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += s->pad1;)
         return false;
     }
     const uint32_t n = s->n, b = s->cur_block;
     const uint32_t size = ((b + 1u) * BLOCK <= n) ? BLOCK : (n & (BLOCK - 1u));
     const uint32_t freqs_off = s->freqs_off;
-    if (c.win_slot != slot) {
+    const bool in_dwin = slot == c.drv_slot && c.dwin_block == b;
+    if (!in_dwin && c.win_slot != slot) {
         const uint64_t data_off = s->data_off;
         const uint32_t off = and_stage(c.lists, data_off + freqs_off, data_off + s->cur_end, c.stage, c.bar, c.phase);
         c.win_slot = slot; c.win_delta = off - freqs_off;
     }
     bool prefix;
-    const uint32_t consumed = and_decode_values<CODEC>(c.stage_off, freqs_off + c.win_delta, size, 0xffffffffu, out_off, c.stack_off, prefix);
+    const uint32_t consumed = in_dwin ? and_decode_values<CODEC>(c.stage_off + STAGE_WORDS * 4u, freqs_off + c.dwin_delta, size, 0xffffffffu, out_off, c.stack_off, prefix)
+                                      : and_decode_values<CODEC>(c.stage_off, freqs_off + c.win_delta, size, 0xffffffffu, out_off, c.stack_off, prefix);
     DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += consumed;)
     return prefix;
 }
@@ -422,16 +473,17 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
     AndWarp* ws = reinterpret_cast<AndWarp*>(base);
     AndList* st = reinterpret_cast<AndList*>(base + sizeof(AndWarp));
     uint32_t* ftmp = reinterpret_cast<uint32_t*>(base + sizeof(AndWarp) + size_t(slots) * sizeof(AndList));
-    uint32_t* stage = ftmp + BLOCK;
-    uint32_t* stack = stage + STAGE_WORDS;
+    uint32_t* stage = ftmp + BLOCK;                 // probe window, then the driver window
+    uint32_t* stack = stage + AND_STAGE_WINDOWS * STAGE_WORDS;
 
     AndCtxT<STATS> c;
     c.fcache_off = smem_offset(stack + SCRATCH_WORDS);
+    c.drv_slot = AND_DRIVER_PREFETCH ? 0u : 0xffffffffu; c.dwin_block = 0xffffffffu; c.dwin_delta = 0; c.dphase = 0;
     c.lists = idx.lists; c.stage = stage; c.bar = &ws->bar;
     c.stage_off = smem_offset(stage); c.stack_off = smem_offset(stack); c.ftmp_off = smem_offset(ftmp);
     c.phase = 0; c.win_slot = 0xffffffffu; c.win_delta = 0;
     c.c_docs_blocks = c.c_freqs_blocks = c.c_bytes_docs = c.c_bytes_freqs = c.c_maxs = c.c_scored = 0;
-    if (lane == 0) { mbar_init(c.bar, 1); fence_mbar_init(); }
+    if (lane == 0) { mbar_init(c.bar, 1); mbar_init(c.bar + 1, 1); fence_mbar_init(); }
     __syncwarp();
 
     while (true) {
@@ -457,7 +509,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             const uint32_t src = batch.ord_size[t0 + lane];
             if (RANKED) ws->qw[lane] = batch.q_weight[t0 + src];
             and_list_setup<CODEC>(idx, &st[lane], batch.term[t0 + src]);
-            if (CODEC == CODEC_PEF) (reinterpret_cast<PefFreqSlot*>(g_smem + c.fcache_off) + lane)->fp = 0xffffffffu;
+            if (CODEC == CODEC_PEF) (reinterpret_cast<PefFreqSlot*>(g_smem + c.fcache_off + PEF_SCAN_SCRATCH_BYTES) + lane)->fp = 0xffffffffu;
         }
         __syncwarp();
 
@@ -476,62 +528,25 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             }
         }
         uint32_t b_begin = first_block;
-        // ---- single-term queries (a tenth of a query log, but whole lists: a fifth of all driver blocks) ----
+        // ---- single-term queries (a tenth of the query log, but whole lists: a fifth of all driver blocks) ----
         if (!RANKED && CODEC != CODEC_PEF && nt == 1) {
             // and_query over one list counts its postings (queries.hpp:58-83 with an empty inner loop): nothing to decode
             matches = min(st[0].n, b_end * BLOCK) - first_block * BLOCK;
             b_begin = b_end;
         }
-        if (RANKED && CODEC == CODEC_OPTPFOR && nt == 1) {
-            // ranked_and over one list is the top-k of qw * doc_term_weight(freq, norm_len[doc]) over its postings.  The freqs
-            // block is decoded FIRST: qw * doc_term_weight(freq, smallest norm_len of the collection) bounds the score of a
-            // posting from above (every fp32 step of bm25.hpp:11-15 is monotone), so once the heap is full a block none of
-            // whose postings can beat the threshold needs neither its docids nor the norm_len gathers.  Same top-k, bit for bit.
-            AndList* s = &st[0];
-            const float qw0 = ws->qw[0];
-            for (; b_begin < b_end; ++b_begin) {
-                const uint32_t b0 = b_begin, l = b0 - first_block;
-                if ((b0 + 1u) * BLOCK > s->n) break;                     // the partial last block: the general path below
-                const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
-                const uint32_t e0 = l ? pe : first_prev_end, e1 = __shfl_sync(FULL, m_end, l);
-                const uint32_t cur_base = (l ? pm : first_prev_max) + 1u, cur_max = __shfl_sync(FULL, m_max, l);
-                const uint32_t off = and_stage(c.lists, s->data_off + e0, s->data_off + e1, c.stage, c.bar, c.phase);
-                c.win_slot = 0xffffffffu;
-                const uint32_t w0 = lds_u32(stage, off);
-                const uint32_t docs_bytes = (w0 >> 26) >= 32u ? 4u * 129u : 4u * (1u + (w0 & 0xffffu) + 4u * (w0 >> 26));     // newpfor.h:204-209,254-286
-                bool prefix;
-                const uint32_t fbytes = and_decode_values<CODEC>(c.stage_off, off + docs_bytes, BLOCK, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
-                const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
-                const uint32_t f[4] = {fv.x + 1u, fv.y + 1u, fv.z + 1u, fv.w + 1u};
-                uint32_t pass = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pass |= uint32_t(topk.would_enter(qw0 * doc_term_weight(f[j], wand.min_norm_len))) << j;
-                DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += fbytes;)
-                if (!__any_sync(FULL, pass)) continue;
-                const uint32_t dbytes = and_decode_values<CODEC>(c.stage_off, off, BLOCK, cur_max - cur_base - (BLOCK - 1u), smem_offset(s->docs), c.stack_off, prefix);
-                uint4 v = reinterpret_cast<uint4*>(s->docs)[lane];
-                v.y += v.x; v.z += v.y; v.w += v.z;
-                const uint32_t incl = warp_inclusive_scan(v.w);
-                const uint32_t add = cur_base + (incl - v.w) + 4u * lane;     // docid_i = base + sum_{k<=i} gap_k + i
-                const uint32_t doc[4] = {v.x + add, v.y + add + 1u, v.z + add + 2u, v.w + add + 3u};
-                __syncwarp();
-                float sc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (pass & (1u << j)) sc[j] = qw0 * doc_term_weight(f[j], __ldg(wand.norm_lens + doc[j]));
-                DS2I_STAT(c.c_docs_blocks += 1; c.c_bytes_docs += dbytes; c.c_scored += __reduce_add_sync(FULL, __popc(pass));)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    unsigned want = __ballot_sync(FULL, (pass & (1u << j)) && topk.would_enter(sc[j]));
-                    while (want) {
-                        const int src = __ffs(want) - 1;
-                        want &= want - 1;
-                        topk.insert(__shfl_sync(FULL, sc[j], src), __shfl_sync(FULL, doc[j], src));
-                    }
-                }
-            }
-        }
         bool exhausted = false;
+        // byte range of driver block b inside the list's data: [end of block b - 1, end of block b)
+        auto driver_range = [&](uint32_t b, uint32_t& e0, uint32_t& e1) {
+            const uint32_t l = b - first_block;
+            const uint32_t pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
+            e0 = l ? pe : first_prev_end; e1 = __shfl_sync(FULL, m_end, l);
+        };
+        c.dwin_block = 0xffffffffu;
+        if (AND_DRIVER_PREFETCH && CODEC != CODEC_PEF && b_begin < b_end) {
+            uint32_t e0, e1;
+            driver_range(b_begin, e0, e1);
+            and_prefetch_driver(c, &st[0], b_begin, e0, e1);
+        }
         for (uint32_t b0 = b_begin; b0 < b_end && !exhausted; ++b0) {
             {
                 const uint32_t l = b0 - first_block;
@@ -560,6 +575,13 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
                     f0[3] -= f0[2]; f0[2] -= f0[1]; f0[1] -= f0[0]; f0[0] -= prev;
                 }
                 __syncwarp();
+            }
+            // everything this block needs of the driver window has been decoded: the next pair is copied while the other
+            // lists are probed (the probes use the other staging window)
+            if (AND_DRIVER_PREFETCH && CODEC != CODEC_PEF && b0 + 1 < b_end) {
+                uint32_t e0, e1;
+                driver_range(b0 + 1, e0, e1);
+                and_prefetch_driver(c, &st[0], b0 + 1, e0, e1);
             }
 
             for (uint32_t i = 1; i < nt; ++i) {
@@ -684,6 +706,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
             }
         }
 
+        if (AND_DRIVER_PREFETCH) and_driver_ready(c);       // a copy still in flight (the loop stopped early) must land before the window is reused
         if (lane == 0) { job.item_counts[ii] = matches; job.item_sizes[ii] = topk.size; }
         if (RANKED && lane < topk.size) {
             job.item_scores[size_t(ii) * 2 * k + lane] = topk.v;

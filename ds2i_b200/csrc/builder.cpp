@@ -14,6 +14,18 @@
 //   compact_elias_fano::write           compact_elias_fano.hpp:68-136
 //   wand_data ctor / map                wand_data.hpp:16-52,71-78
 //
+// ATTRIBUTION.  Byte-identical output leaves no freedom in the encoders: every decision the reference takes (which b OptPFD
+// picks, where a partition ends, which of three codes a partition gets, where a sampled pointer goes) has to be taken the same
+// way.  The following functions are therefore close restatements of the reference's encoders — same algorithm, same
+// arithmetic, in places the same variable roles — and are offline host tooling, not part of the query path:
+//   optpfor_find_best_b / collect_exceptions / s16_encode   block_codecs.hpp:156-182, FastPFor newpfor.h:149-211, simple16.h:181-420
+//   write_posting_list                                       block_posting_list.hpp:14-53
+//   bit_writer32 / interpolative_encode                      interpolative_coding.hpp:11-73, block_codecs.hpp:105-125
+//   ef_write                                                 compact_elias_fano.hpp:69-135
+//   rb_write / partition_bits / choose_partitions / partitioned_write   compact_ranked_bitvector.hpp:56-115, indexed_sequence.hpp:24-84,
+//                                                            optimal_partition.hpp:69-121, partitioned_sequence.hpp:22-120
+// Everything around them (the parallel chunked build, the list sources, the synthetic generator, sharding, the file writer) is ours.
+//
 //   ds2i_build gen   <prefix> <num_docs> <num_terms> <seed> [scale=0.35] [nqueries=10000] [qseed]
 //   ds2i_build index <block_optpfor|block_interpolative|opt> <collection prefix> <out.idx> [threads]
 //   ds2i_build wand  <collection prefix> <out.wand> [threads]

@@ -738,9 +738,9 @@ static int launch_query(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
 }
 
 #ifndef DS2I_AND_MIN_CTAS
-#define DS2I_AND_MIN_CTAS 6
+#define DS2I_AND_MIN_CTAS 7
 #endif
-constexpr int AND_MIN_CTAS = DS2I_AND_MIN_CTAS;     // 6: 24 resident warps per SM (<= 80 registers per thread)
+constexpr int AND_MIN_CTAS = DS2I_AND_MIN_CTAS;     // 7: 28 resident warps per SM, <= 72 registers per thread (measured: 5 / 6 / 7 / 8 CTAs -> ranked_and 16.98 / 16.14 / 15.77 / 16.9 ms)
 // the Elias-Fano window decoders carry a wide partition descriptor (PefBody): fewer, fatter warps beat spilling it
 #ifndef DS2I_PEF_MIN_CTAS
 #define DS2I_PEF_MIN_CTAS 4
@@ -797,7 +797,7 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
 }
 
 #ifndef DS2I_UNION_MIN_CTAS
-#define DS2I_UNION_MIN_CTAS 6
+#define DS2I_UNION_MIN_CTAS 7
 #endif
 constexpr int UNION_MIN_CTAS = DS2I_UNION_MIN_CTAS;
 

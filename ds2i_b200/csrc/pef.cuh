@@ -226,6 +226,56 @@ __device__ __forceinline__ uint32_t pef_scan_ones(Bits const& bits, uint64_t sta
     return extra;
 }
 
+// The same with the words of a step parked in shared memory (scratch_off: 32 x u64 words + 32 x u32 first ordinals = 384 B per
+// warp): every lane resolves FOUR CONSECUTIVE ordinals — one search for the word of the first, one select to drop the bits
+// before it, then next-set-bit steps — instead of four independent search + select rounds.  Output index = ordinal - r0 as above.
+template <class Bits>
+__device__ __forceinline__ uint32_t pef_scan_ones_smem(Bits const& bits, uint64_t start, uint64_t origin, uint32_t r0, uint32_t cnt, uint32_t* out, uint32_t scratch_off) {
+    const unsigned lane = lane_id();
+    uint64_t* wbuf = reinterpret_cast<uint64_t*>(g_smem + scratch_off);
+    uint32_t* ebuf = reinterpret_cast<uint32_t*>(wbuf + 32);
+    uint64_t wbase = start >> 6;
+    uint32_t seen = 0, extra = 0;
+    const uint32_t r1 = r0 + cnt;
+    const uint32_t i0 = 4u * lane, i1 = min(cnt, i0 + 4u + ((lane == 31u && cnt > 128u) ? 1u : 0u));     // my output indices [i0, i1)
+    bool first = true;
+    while (seen < r1) {
+        uint64_t w = bits.word(wbase + lane);
+        if (first && lane == 0) w &= ~uint64_t(0) << (start & 63);
+        first = false;
+        const uint32_t pc = __popcll(w);
+        const uint32_t incl = warp_inclusive_scan(pc);
+        const uint32_t excl = seen + incl - pc;
+        const uint32_t total = seen + __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        wbuf[lane] = w; ebuf[lane] = excl;
+        __syncwarp();
+        uint32_t o = max(r0 + i0, seen);
+        const uint32_t hi = min(r0 + i1, total);
+        if (i0 < i1 && o < hi) {
+            // word holding ordinal o: the largest t with ebuf[t] <= o (words without set bits share their first ordinal with
+            // their successor; the search lands on the last of them, the one that owns the ordinal)
+            uint32_t t = 0;
+#pragma unroll
+            for (uint32_t s = 16; s >= 1; s >>= 1)
+                if (ebuf[t + s] <= o) t += s;
+            uint64_t cur = wbuf[t];
+            const uint32_t k = o - ebuf[t];
+            if (k) cur &= ~uint64_t(0) << select_in_word(cur, k);            // drop the k set bits before it
+            for (; o < hi; ++o) {
+                while (!cur) cur = wbuf[++t];
+                const uint32_t p = uint32_t((wbase + t) * 64 + uint32_t(__ffsll((long long)cur) - 1) - origin);
+                cur &= cur - 1;
+                if (o - r0 < 128u) out[o - r0] = p; else extra = p;
+            }
+        }
+        seen = total;
+        wbase += 32;
+    }
+    __syncwarp();
+    return cnt > 128u ? __shfl_sync(FULL, extra, 31) : 0u;
+}
+
 // count of ZERO bits wanted: position (relative to origin) of the zero with ordinal z (0 = first zero
 // at or after start), z < 2^log_sampling0 + slack.  Returns warp-uniformly.
 template <class Bits>
@@ -258,7 +308,7 @@ __device__ __forceinline__ uint64_t pef_select_zero(Bits const& bits, uint64_t s
 // element i0 - 1 is decoded along (one scan instead of two) and returned, warp-uniformly; otherwise 0 is returned.
 template <class Bits>
 __device__ __forceinline__ uint32_t pef_decode_range(Bits const& bits, PefPart const& p, PefBody const& b, uint32_t i0, uint32_t cnt, uint32_t* out,
-                                                     bool with_prev = false) {
+                                                     bool with_prev = false, uint32_t scratch_off = 0 /* 384 B of shared memory: the faster scan */) {
     const unsigned lane = lane_id();
     if (b.type == PEF_AO) {
 #pragma unroll
@@ -282,7 +332,7 @@ __device__ __forceinline__ uint32_t pef_decode_range(Bits const& bits, PefPart c
         start = origin + ptr;
         r0 = f0 - (s << b.log_s1);
     }
-    const uint32_t extra = pef_scan_ones(bits, start, origin, r0, total, out);
+    const uint32_t extra = scratch_off ? pef_scan_ones_smem(bits, start, origin, r0, total, out, scratch_off) : pef_scan_ones(bits, start, origin, r0, total, out);
     // positions -> values; with_prev moves every value one slot down (element f0 goes to the return register), so all
     // positions are read before any value is written
     uint32_t pos[4];
@@ -371,9 +421,9 @@ __device__ __forceinline__ PefSeqParams pef_params(PefSeq const& s) {
 // inlined copy per site (~2.5 k instructions each) made them fetch-bound — 34 issue slots lost to instruction misses per issue.
 // with_prev: also returns element i0 - 1 (i0 > 0).
 __device__ __noinline__ uint32_t pef_window_values(PefSeqParams seq, AnyBits bits, PefPart p, bool strict, uint32_t i0, uint32_t cnt, uint32_t out_off,
-                                                   bool with_prev, uint32_t known_type = 0xffffffffu) {
+                                                   bool with_prev, uint32_t scratch_off, uint32_t known_type = 0xffffffffu) {
     const PefBody b = pef_open_body(seq, bits, p, strict, known_type);
-    return pef_decode_range(bits, p, b, i0, cnt, smem_words(out_off), with_prev);
+    return pef_decode_range(bits, p, b, i0, cnt, smem_words(out_off), with_prev, scratch_off);
 }
 
 // the same straight from HBM (what the literal enumerator and the full-decode kernels use)

@@ -60,13 +60,13 @@ struct TopKShared {
 struct UnionWarp {
     float qw[MAX_TERMS];
     float ub[MAX_TERMS];    // upper bounds, inflated by one part in 2^19: a bound that is itself a rounded sum stays a bound
-    uint64_t bar;
-    uint64_t pad;
+    uint64_t bar;           // mbarrier of the probe staging window
+    uint64_t dbar;          // mbarrier of the driving list's staging window
 };
 
 __host__ __device__ constexpr size_t union_warp_smem_bytes(int slots, bool pef = false) {
-    return sizeof(UnionWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 +
-           (pef ? size_t(slots) * sizeof(PefFreqSlot) : 0);
+    return sizeof(UnionWarp) + size_t(slots) * sizeof(AndList) + BLOCK * 4 /* freqs */ + AND_STAGE_WINDOWS * STAGE_WORDS * 4 /* probe (+ driver) window */ +
+           SCRATCH_WORDS * 4 + (pef ? size_t(slots) * sizeof(PefFreqSlot) + PEF_SCAN_SCRATCH_BYTES : 0);
 }
 
 // Look the candidates in `alive` up in list s (slot i).  score_mode: hits add the list's BM25 term; otherwise hits
@@ -151,16 +151,17 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
     UnionWarp* ws = reinterpret_cast<UnionWarp*>(base);
     AndList* st = reinterpret_cast<AndList*>(base + sizeof(UnionWarp));
     uint32_t* ftmp = reinterpret_cast<uint32_t*>(base + sizeof(UnionWarp) + size_t(slots) * sizeof(AndList));
-    uint32_t* stage = ftmp + BLOCK;
-    uint32_t* stack = stage + STAGE_WORDS;
+    uint32_t* stage = ftmp + BLOCK;                 // probe window, then the driver window
+    uint32_t* stack = stage + AND_STAGE_WINDOWS * STAGE_WORDS;
 
     AndCtxT<STATS> c;
     c.fcache_off = smem_offset(stack + SCRATCH_WORDS);
+    c.drv_slot = 0xffffffffu; c.dwin_block = 0xffffffffu; c.dwin_delta = 0; c.dphase = 0;
     c.lists = idx.lists; c.stage = stage; c.bar = &ws->bar;
     c.stage_off = smem_offset(stage); c.stack_off = smem_offset(stack); c.ftmp_off = smem_offset(ftmp);
     c.phase = 0; c.win_slot = 0xffffffffu; c.win_delta = 0;
     c.c_docs_blocks = c.c_freqs_blocks = c.c_bytes_docs = c.c_bytes_freqs = c.c_maxs = c.c_scored = 0;
-    if (lane == 0) { mbar_init(c.bar, 1); fence_mbar_init(); }
+    if (lane == 0) { mbar_init(c.bar, 1); mbar_init(c.bar + 1, 1); fence_mbar_init(); }
     __syncwarp();
     constexpr float INFLATE = 1.0f + 1.0f / 524288.0f;
 
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
             ws->qw[lane] = batch.q_weight[t0 + src];
             ws->ub[lane] = __ldg(job.ub + t0 + lane) * INFLATE;
             and_list_setup<CODEC>(idx, &st[lane], batch.term[t0 + src]);
-            if (CODEC == CODEC_PEF) (reinterpret_cast<PefFreqSlot*>(g_smem + c.fcache_off) + lane)->fp = 0xffffffffu;
+            if (CODEC == CODEC_PEF) (reinterpret_cast<PefFreqSlot*>(g_smem + c.fcache_off + PEF_SCAN_SCRATCH_BYTES) + lane)->fp = 0xffffffffu;
         }
         __syncwarp();
 
@@ -226,54 +227,17 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                 // refresh the shared floor (queries.hpp:568-574: the non-essential prefix only grows)
                 topk.floor_ = fmaxf(topk.floor_, read_threshold());
                 if (!(ub_e > topk.bar())) { stop = true; break; }
-                uint32_t f0[4] = {0, 0, 0, 0}, pass = 0xfu;
-                bool have_f0 = false;
                 {
                     const uint32_t l = b0 - c0;
                     const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
-                    const uint32_t e0 = l ? pe : first_prev_end, e1 = __shfl_sync(FULL, m_end, l);
-                    const uint32_t prev_max = l ? pm : first_prev_max, cur_max = __shfl_sync(FULL, m_max, l);
-                    if (CODEC == CODEC_OPTPFOR && (b0 + 1u) * BLOCK <= sd->n) {
-                        // The driving list's freqs block FIRST.  A document owned by list e scores at most
-                        // qw_e * doc_term_weight(freq, smallest norm_len of the collection) + ub[e-1]: postings whose bound cannot
-                        // beat the bar are dropped before anything is probed or gathered, and a block without a survivor does not
-                        // even have its docids decoded.  (Same top-k: a dropped document could not have entered.)
-                        const uint32_t off = and_stage(c.lists, sd->data_off + e0, sd->data_off + e1, c.stage, c.bar, c.phase);
-                        c.win_slot = e; c.win_delta = off - e0;
-                        const uint32_t w0 = lds_u32(stage, off);
-                        const uint32_t docs_bytes = (w0 >> 26) >= 32u ? 4u * 129u : 4u * (1u + (w0 & 0xffffu) + 4u * (w0 >> 26));     // newpfor.h:204-209,254-286
-                        bool prefix;
-                        const uint32_t fbytes = and_decode_values<CODEC>(c.stage_off, off + docs_bytes, BLOCK, 0xffffffffu, c.ftmp_off, c.stack_off, prefix);
-                        const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
-                        f0[0] = fv.x; f0[1] = fv.y; f0[2] = fv.z; f0[3] = fv.w;
-                        have_f0 = true;
-                        const float below = e ? ws->ub[e - 1] : 0.f, bar = topk.bar();
-                        pass = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) pass |= uint32_t((qw_e * doc_term_weight(f0[j] + 1u, wand.min_norm_len) + below) * INFLATE > bar) << j;
-                        DS2I_STAT(c.c_freqs_blocks += 1; c.c_bytes_freqs += fbytes;)
-                        if (!__any_sync(FULL, pass)) continue;
-                        const uint32_t cur_base = prev_max + 1u;
-                        const uint32_t dbytes = and_decode_values<CODEC>(c.stage_off, off, BLOCK, cur_max - cur_base - (BLOCK - 1u), smem_offset(sd->docs), c.stack_off, prefix);
-                        uint4 v = reinterpret_cast<uint4*>(sd->docs)[lane];
-                        v.y += v.x; v.z += v.y; v.w += v.z;
-                        const uint32_t incl = warp_inclusive_scan(v.w);
-                        const uint32_t add = cur_base + (incl - v.w) + 4u * lane;     // docid_i = base + sum_{k<=i} gap_k + i
-                        v.x += add; v.y += add + 1u; v.z += add + 2u; v.w += add + 3u;
-                        reinterpret_cast<uint4*>(sd->docs)[lane] = v;
-                        if (lane == 0) *reinterpret_cast<uint4*>(&sd->cur_block) = make_uint4(b0, cur_max, e1, e0 + dbytes);
-                        __syncwarp();
-                        DS2I_STAT(c.c_docs_blocks += 1; c.c_bytes_docs += dbytes;)
-                    } else {
-                        and_decode_docs<CODEC>(c, idx, sd, e, b0, e0, e1, prev_max, cur_max);
-                    }
+                    and_decode_docs<CODEC>(c, idx, sd, e, b0, l ? pe : first_prev_end, __shfl_sync(FULL, m_end, l), l ? pm : first_prev_max,
+                                           __shfl_sync(FULL, m_max, l));
                 }
                 const uint4 cv = reinterpret_cast<const uint4*>(sd->docs)[lane];
                 const uint32_t cand[4] = {cv.x, cv.y, cv.z, cv.w};
                 uint32_t alive = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) alive |= (cand[j] != 0xffffffffu) << j;
-                alive &= pass;
                 float norm_len[4] = {0.f, 0.f, 0.f, 0.f}, score[4] = {0.f, 0.f, 0.f, 0.f};
 
                 // every list from the highest bound down.  Lists above e own the documents they share with e (a hit
@@ -284,16 +248,14 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (alive & (1u << j)) norm_len[j] = __ldg(wand.norm_lens + cand[j]);
-                        if (!have_f0) {
-                            const bool prefix = and_decode_freqs<CODEC>(c, idx, sd, e, c.ftmp_off);
-                            const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
-                            f0[0] = fv.x; f0[1] = fv.y; f0[2] = fv.z; f0[3] = fv.w;
-                            if (prefix) {
-                                const uint32_t prev = lane ? ftmp[4 * lane - 1] : 0u;
-                                f0[3] -= f0[2]; f0[2] -= f0[1]; f0[1] -= f0[0]; f0[0] -= prev;
-                            }
-                            __syncwarp();
+                        const bool prefix = and_decode_freqs<CODEC>(c, idx, sd, e, c.ftmp_off);
+                        const uint4 fv = reinterpret_cast<const uint4*>(ftmp)[lane];
+                        uint32_t f0[4] = {fv.x, fv.y, fv.z, fv.w};
+                        if (prefix) {
+                            const uint32_t prev = lane ? ftmp[4 * lane - 1] : 0u;
+                            f0[3] -= f0[2]; f0[2] -= f0[1]; f0[1] -= f0[0]; f0[0] -= prev;
                         }
+                        __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (alive & (1u << j)) score[j] = qw_e * doc_term_weight(f0[j] + 1u, norm_len[j]);
