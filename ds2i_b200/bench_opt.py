@@ -45,7 +45,8 @@ def legs(d, args, paths, queries, qidx, wdata, peak, measure, line_of, cpu_basel
     for j in (0, 3, 6, 9, 12):
         # every list's bound sequence is cut into runs of CHUNK calls, each run driven through its own enumerator (opened at
         # the list start): one warp per list alone would leave most of the 148 SMs idle
-        CHUNK = 512
+        total_calls = sum((int(offs[i + 1]) - int(offs[i]) + (1 << j) - 1) >> j for i in range(GL))
+        CHUNK = max(8, min(512, total_calls // 16384))       # >= ~16k independent cursors whenever the sweep has that many calls
         bounds, which = [], []
         for i in range(GL):
             bb = docs[int(offs[i]):int(offs[i + 1])][::1 << j].astype(np.uint64) + 1
@@ -66,7 +67,7 @@ def legs(d, args, paths, queries, qidx, wdata, peak, measure, line_of, cpu_basel
                 f.write(np.asarray(b, dtype="<u8").tobytes())
         ref = json.loads(ref_tool("geqbench", "opt", paths["opt"], spec, cores, 1).strip().splitlines()[-1])
         dev_sum = int(gd.sum() + gf.sum())
-        sweeps["skip_%d" % (1 << j)] = {"calls": calls, "enumerators": len(bounds), "ms": m, "calls_per_s": calls / (m * 1e-3),
+        sweeps["skip_%d" % (1 << j)] = {"calls": calls, "enumerators": len(bounds), "calls_per_enumerator": CHUNK, "ms": m, "calls_per_s": calls / (m * 1e-3),
                                         "postings_skipped_per_s": calls * (1 << j) / (m * 1e-3),
                                         "cpu_calls_per_s": ref["calls_per_s"], "cpu_cores": cores,
                                         "parity_checksum_equal": dev_sum == ref["checksum"]}

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -466,14 +468,82 @@ extern "C" int ds2i_gpu_batch_prepare(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, c
     return batch_prepare_impl(ix, wand, terms, query_offsets, nq, 3u, out);
 }
 
-// number of host threads for the per-query preparation (DS2I_GPU_HOST_THREADS overrides; small batches stay single-threaded)
-static unsigned prepare_threads(size_t nq) {
-    static const unsigned hw = [] {
+// Persistent host threads for the per-query preparation: spawning std::threads per batch cost more than the work they did
+// (1.1 ms for a 10k-query batch on 16 threads, against 2.2 ms single-threaded).  run(n, fn) calls fn(0) .. fn(n-1), fn(0) on
+// the caller; it returns when all are done.  One batch is prepared at a time per process (the pool is a shared resource).
+class host_pool {
+public:
+    static host_pool& get() { static host_pool p; return p; }
+    unsigned size() const { return unsigned(m_threads.size()) + 1; }
+    template <typename F>
+    void run(unsigned n, F&& fn) {
+        if (n <= 1) { if (n) fn(0u); return; }
+        std::unique_lock<std::mutex> user(m_user);              // one parallel region at a time
+        {
+            std::lock_guard<std::mutex> lk(m_mu);
+            m_fn = [&fn](unsigned i) { fn(i); };
+            m_n = n; m_next = 1; m_done = 1; ++m_epoch;          // index 0 runs on the caller
+        }
+        m_cv.notify_all();
+        fn(0u);
+        work();
+        std::unique_lock<std::mutex> lk(m_mu);
+        m_cv_done.wait(lk, [&] { return m_done >= m_n + 0u && m_active == 0; });
+        m_fn = nullptr;
+    }
+private:
+    host_pool() {
         unsigned n = std::thread::hardware_concurrency();
         if (const char* ev = getenv("DS2I_GPU_HOST_THREADS")) n = unsigned(std::max(1, atoi(ev)));
-        return std::max(1u, std::min(n, 16u));
-    }();
-    return unsigned(std::max<size_t>(1, std::min<size_t>(hw, nq / 512)));
+        n = std::max(1u, std::min(n, 16u));
+        for (unsigned t = 1; t < n; ++t) m_threads.emplace_back([this] { loop(); });
+    }
+    ~host_pool() {
+        { std::lock_guard<std::mutex> lk(m_mu); m_stop = true; }
+        m_cv.notify_all();
+        for (auto& t : m_threads) t.join();
+    }
+    void work() {
+        while (true) {
+            unsigned i;
+            std::function<void(unsigned)> fn;
+            {
+                std::lock_guard<std::mutex> lk(m_mu);
+                if (m_next >= m_n) return;
+                i = m_next++; fn = m_fn;
+            }
+            fn(i);
+            std::lock_guard<std::mutex> lk(m_mu);
+            if (++m_done >= m_n) m_cv_done.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(m_mu);
+                m_cv.wait(lk, [&] { return m_stop || m_epoch != seen; });
+                if (m_stop) return;
+                seen = m_epoch; ++m_active;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(m_mu);
+            --m_active;
+            m_cv_done.notify_all();
+        }
+    }
+    std::vector<std::thread> m_threads;
+    std::mutex m_mu, m_user;
+    std::condition_variable m_cv, m_cv_done;
+    std::function<void(unsigned)> m_fn;
+    unsigned m_n = 0, m_next = 0, m_done = 0, m_active = 0;
+    uint64_t m_epoch = 0;
+    bool m_stop = false;
+};
+
+// number of host threads for the per-query preparation (DS2I_GPU_HOST_THREADS overrides; small batches stay single-threaded)
+static unsigned prepare_threads(size_t nq) {
+    return unsigned(std::max<size_t>(1, std::min<size_t>(host_pool::get().size(), nq / 512)));
 }
 
 // what one host thread produces for its contiguous range of queries
@@ -552,13 +622,9 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     // ---- per-query host work, on several threads (contiguous ranges, so the parts concatenate in query order)
     const unsigned nthreads = prepare_threads(nq);
     std::vector<prep_part> parts(nthreads);
-    {
-        std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nthreads; ++t)
-            pool.emplace_back(prepare_range, ix, wand, terms, query_offsets, nq * t / nthreads, nq * (t + 1) / nthreads, std::ref(parts[t]));
-        prepare_range(ix, wand, terms, query_offsets, 0, nq / nthreads, parts[0]);
-        for (auto& th : pool) th.join();
-    }
+    host_pool::get().run(nthreads, [&](unsigned t) {
+        prepare_range(ix, wand, terms, query_offsets, nq * t / nthreads, nq * (t + 1) / nthreads, parts[t]);
+    });
     size_t nterms_total = 0;
     int max_terms = 1;
     for (auto const& pt : parts) {
@@ -608,10 +674,20 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
             }
         }
     }
-    // processing order: costliest queries first (ties keep the query order)
+    // processing order: costliest queries first.  The order only steers the scheduler (longest work first), so a stable
+    // counting sort on a 7-bit logarithmic key (exponent + two mantissa bits of the cost) replaces the comparison sort
+    // that used to be a third of the host time of a 10k-query batch.
     {
-        std::iota(sched, sched + nq, 0u);
-        std::stable_sort(sched, sched + nq, [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+        auto key_of = [](uint64_t c) -> uint32_t {
+            if (c < 4) return uint32_t(c);
+            const uint32_t e = 63u - uint32_t(__builtin_clzll(c));
+            return 4u * (e - 1u) + uint32_t((c >> (e - 2u)) & 3u);          // monotone in c, < 256
+        };
+        uint32_t count[257] = {0};
+        for (size_t q = 0; q < nq; ++q) count[256u - key_of(cost[q])] += 1;      // descending
+        uint32_t pos = 0;
+        for (uint32_t kx = 0; kx <= 256; ++kx) { const uint32_t c = count[kx]; count[kx] = pos; pos += c; }
+        for (size_t q = 0; q < nq; ++q) sched[count[256u - key_of(cost[q])]++] = uint32_t(q);
     }
 
     const double tp1 = now_ms();
@@ -1039,7 +1115,7 @@ extern "C" int ds2i_gpu_query_batch_docids(ds2i_gpu_index* ix, ds2i_gpu_wand* wa
     if (rc != DS2I_OK) return rc;
     std::unique_ptr<ds2i_gpu_batch> guard(b);
     double t1 = now_ms();
-    rc = ds2i_gpu_batch_run(b, op, k, out_elapsed_ms);
+    rc = ds2i_gpu_batch_run_ex(b, op, k, DS2I_RUN_NO_STATS, out_elapsed_ms);     // the batch dies with the call: nobody could read its counters
     if (rc != DS2I_OK) return rc;
     double t2 = now_ms();
     rc = ds2i_gpu_batch_fetch(b, out_counts, out_scores);
