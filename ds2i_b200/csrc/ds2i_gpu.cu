@@ -877,11 +877,11 @@ static int launch_and_block_codec(ds2i_gpu_batch* b, DevBatch const& db, uint32_
 #endif
 constexpr int UNION_MIN_CTAS = DS2I_UNION_MIN_CTAS;
 
-template <int CODEC, bool STATS = true>
+template <int CODEC, bool STATS = true, int MODE = UNION_TOPK>
 static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
     ds2i_gpu_index* ix = b->index;
     const int warps = 4;
-    auto kern = union_drive_kernel<CODEC, CODEC == CODEC_PEF ? DS2I_PEF_MIN_CTAS : UNION_MIN_CTAS, STATS>;
+    auto kern = union_drive_kernel<CODEC, CODEC == CODEC_PEF ? DS2I_PEF_MIN_CTAS : UNION_MIN_CTAS, STATS, MODE>;
     size_t smem = S16_TAB_BYTES + warps * union_warp_smem_bytes(b->max_terms, CODEC == CODEC_PEF);
     int per_sm = 0;
     int orc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), warps * 32, smem, &per_sm);
@@ -896,9 +896,30 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
     }
     CUDA_TRY(cudaMemsetAsync(b->un_threshold.p, 0, std::max<size_t>(b->nq, 1) * sizeof(uint32_t)));
     UnionJob job{b->un_gstart.p, b->un_gterm.p, b->un_gquery.p, b->un_gbase.p, b->un_ub.p, b->n_un_groups, b->n_un_items, b->un_item_blocks, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
-    if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, b->wand->dev, db, job, k, b->max_terms); b->launches += 1; }
-    merge_union_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_scores.p, k, b->out_counts.p, b->out_scores.p, b->out_docids.p);
+    const DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr, 0.f};
+    if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, b->max_terms); b->launches += 1; }
+    if (MODE == UNION_COUNT) merge_union_counts_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->out_counts.p);
+    else merge_union_items_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->un_item_scores.p, k, b->out_counts.p, b->out_scores.p, b->out_docids.p);
     return DS2I_OK;
+}
+
+// or / ranked_or on the block-parallel union machinery (every index type)
+template <int MODE>
+static int launch_union_mode(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
+    switch (b->index->kind == KIND_PEF ? int(CODEC_PEF) : b->index->codec) {      // (an Elias-Fano index keeps its variant in `codec`)
+        case CODEC_OPTPFOR: return launch_union_block<CODEC_OPTPFOR, true, MODE>(b, db, k);
+#ifndef DS2I_DEV_FAST_BUILD
+        case CODEC_VARINT: return launch_union_block<CODEC_VARINT, true, MODE>(b, db, k);
+        case CODEC_INTERPOLATIVE: return launch_union_block<CODEC_INTERPOLATIVE, true, MODE>(b, db, k);
+        case CODEC_QMX: return launch_union_block<CODEC_QMX, true, MODE>(b, db, k);
+        case CODEC_MIXED: return launch_union_block<CODEC_MIXED, true, MODE>(b, db, k);
+#endif
+        case CODEC_PEF: return launch_union_block<CODEC_PEF, true, MODE>(b, db, k);
+    }
+    return fail(DS2I_E_UNSUPPORTED, "unknown codec");
+}
+static int launch_union_exhaustive(ds2i_gpu_batch* b, DevBatch const& db, int op, uint32_t k) {
+    return op == OP_OR ? launch_union_mode<UNION_COUNT>(b, db, k) : launch_union_mode<UNION_EXHAUSTIVE>(b, db, k);
 }
 
 template <int CODEC>
@@ -948,6 +969,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
         }
         else if (ix->kind == KIND_PEF && fast && (op == OP_WAND || op == OP_MAXSCORE) && (b->items_built & 2u))
             rc = no_stats ? launch_union_block<CODEC_PEF, false>(b, db, k) : launch_union_block<CODEC_PEF>(b, db, k);
+        else if (fast && (op == OP_OR || op == OP_RANKED_OR) && (b->items_built & 2u)) rc = launch_union_exhaustive(b, db, op, k);
         else if (ix->kind == KIND_PEF) rc = pef_launch_query(*ix->pef, b->wand ? b->wand->dev : DevWand{nullptr, nullptr, 0.f}, db, op, k, b->max_terms, ix->sm_count, g_last_error);
         else if (!(flags & DS2I_RUN_FAITHFUL) && (op == OP_AND || op == OP_RANKED_AND) && (b->items_built & 1u)) {
             rc = op == OP_AND ? launch_and_block_codec<false>(b, db, k, no_stats) : launch_and_block_codec<true>(b, db, k, no_stats);
@@ -1110,7 +1132,7 @@ extern "C" int ds2i_gpu_query_batch_docids(ds2i_gpu_index* ix, ds2i_gpu_wand* wa
     const bool trace = trace_on();
     double t0 = now_ms();
     ds2i_gpu_batch* b = nullptr;
-    unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE) ? 2u : 0u;
+    unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE || op == OP_OR || op == OP_RANKED_OR) ? 2u : 0u;
     int rc = batch_prepare_impl(ix, wand, terms, query_offsets, nq, which, &b);
     if (rc != DS2I_OK) return rc;
     std::unique_ptr<ds2i_gpu_batch> guard(b);
@@ -1517,7 +1539,7 @@ extern "C" int ds2i_gpu_group_query_batch(ds2i_gpu_group* g, int op, uint32_t k,
     std::vector<int> rcs(G, DS2I_OK);
     std::vector<std::string> errs(G);
     std::vector<float> kernel_ms(G, 0.f);
-    const unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE) ? 2u : 0u;
+    const unsigned which = (op == OP_AND || op == OP_RANKED_AND) ? 1u : (op == OP_WAND || op == OP_MAXSCORE || op == OP_OR || op == OP_RANKED_OR) ? 2u : 0u;
     auto work = [&](size_t s) {
         static const uint32_t no_terms = 0;
         const uint32_t* tp = shard_terms[s].empty() ? &no_terms : shard_terms[s].data();

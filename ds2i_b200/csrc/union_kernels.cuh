@@ -140,7 +140,14 @@ __device__ __forceinline__ void union_probe(Ctx& c, DevIndex const& idx, AndList
     }
 }
 
-template <int CODEC, int MIN_CTAS, bool STATS = true>
+// MODE: what is done with the documents a list owns.
+//   UNION_TOPK        wand_query / maxscore_query: dynamic pruning against the query's shared threshold (above)
+//   UNION_EXHAUSTIVE  ranked_or_query (queries.hpp:404-476): every document of the union is scored in full, no pruning —
+//                     the exhaustive cross-check of the pruned operators, on the same machinery
+//   UNION_COUNT       or_query (queries.hpp:88-131): the size of the union = documents each list owns, summed; docids only
+enum : int { UNION_TOPK = 0, UNION_EXHAUSTIVE = 1, UNION_COUNT = 2 };
+
+template <int CODEC, int MIN_CTAS, bool STATS = true, int MODE = UNION_TOPK>
 __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx, DevWand wand, DevBatch batch, UnionJob job, uint32_t k, int slots) {
     s16_table_init(smem_words(0));
     __syncthreads();
@@ -189,12 +196,13 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
 
         TopKShared topk;
         topk.init(k);
-        topk.floor_ = read_threshold();
+        if (MODE == UNION_TOPK) topk.floor_ = read_threshold();
         const float ub_e = __ldg(job.ub + t0 + e) * INFLATE;
-        if (!(ub_e > topk.floor_)) {           // list e is non-essential already: nothing it owns can enter
+        if (MODE == UNION_TOPK && !(ub_e > topk.floor_)) {           // list e is non-essential already: nothing it owns can enter
             if (lane == 0) job.item_sizes[rslot] = 0;
             continue;
         }
+        uint32_t owned = 0;                    // UNION_COUNT: documents of this item that no higher list holds
 
         // slot i <- i-th list by increasing max_weight (queries.hpp:521-524, the reference's own std::sort order)
         c.win_slot = 0xffffffffu;
@@ -224,9 +232,11 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                 if (c0) { const uint2 en = __ldg(bd0 + c0 - 1); first_prev_max = en.x; first_prev_end = en.y; }
             }
             for (uint32_t b0 = c0; b0 < c1; ++b0) {
-                // refresh the shared floor (queries.hpp:568-574: the non-essential prefix only grows)
-                topk.floor_ = fmaxf(topk.floor_, read_threshold());
-                if (!(ub_e > topk.bar())) { stop = true; break; }
+                if (MODE == UNION_TOPK) {
+                    // refresh the shared floor (queries.hpp:568-574: the non-essential prefix only grows)
+                    topk.floor_ = fmaxf(topk.floor_, read_threshold());
+                    if (!(ub_e > topk.bar())) { stop = true; break; }
+                }
                 {
                     const uint32_t l = b0 - c0;
                     const uint32_t pm = __shfl_sync(FULL, m_max, (l + 31) & 31), pe = __shfl_sync(FULL, m_end, (l + 31) & 31);
@@ -244,6 +254,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                 // drops the candidate); at e the survivors get their own term; lists below e complete the score
                 // while score + ub[i] can still enter (queries.hpp:557-566)
                 for (uint32_t i = nt; i-- > 0;) {
+                    if (MODE == UNION_COUNT && i == e) break;           // the ownership probes are all a count needs
                     if (i == e) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                         DS2I_STAT(c.c_scored += __reduce_add_sync(FULL, __popc(alive));)
                         continue;
                     }
-                    if (i < e) {
+                    if (MODE == UNION_TOPK && i < e) {
                         const float bar = topk.bar(), ubi = ws->ub[i];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -273,6 +284,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                     if (i > e && !__any_sync(FULL, alive)) break;
                 }
 
+                if (MODE == UNION_COUNT) { owned += __reduce_add_sync(FULL, __popc(alive)); continue; }
                 // heap: only scores that can still enter
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -283,15 +295,15 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
                         topk.insert(__shfl_sync(FULL, score[j], src), __shfl_sync(FULL, cand[j], src));
                     }
                 }
-                if (topk.t.size == topk.t.k && topk.t.thr > published) {
+                if (MODE == UNION_TOPK && topk.t.size == topk.t.k && topk.t.thr > published) {
                     published = topk.t.thr;
                     if (lane == 0) atomicMax(job.query_threshold + q, __float_as_uint(published));
                 }
             }
         }
 
-        if (lane == 0) job.item_sizes[rslot] = topk.t.size;
-        if (lane < topk.t.size) {
+        if (lane == 0) job.item_sizes[rslot] = MODE == UNION_COUNT ? owned : topk.t.size;
+        if (MODE != UNION_COUNT && lane < topk.t.size) {
             job.item_scores[size_t(rslot) * 2 * k + lane] = topk.t.v;
             reinterpret_cast<uint32_t*>(job.item_scores)[size_t(rslot) * 2 * k + k + lane] = topk.t.id;
         }
@@ -340,6 +352,17 @@ __global__ void __launch_bounds__(128) merge_union_items_kernel(const uint32_t* 
         out_scores[size_t(q) * k + lane] = lane < topk.size ? topk.v : 0.f;
         out_docids[size_t(q) * k + lane] = lane < topk.size ? topk.id : 0xffffffffu;
     }
+}
+
+// or_query: the union's size is the sum of what each (list, block run) item owns
+__global__ void __launch_bounds__(128) merge_union_counts_kernel(const uint32_t* item_begin /* nq+1 */, uint32_t nq, const uint32_t* item_sizes, uint64_t* out_counts) {
+    const unsigned lane = lane_id();
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    unsigned long long total = 0;
+    for (uint32_t it = item_begin[q] + lane; it < item_begin[q + 1]; it += 32) total += item_sizes[it];
+    for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+    if (lane == 0) out_counts[q] = total;
 }
 
 }  // namespace ds2i_gpu

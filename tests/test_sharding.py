@@ -107,7 +107,7 @@ def test_sharded_queries_equal_the_unsharded_reference(native_lib, builder, mini
         assert np.array_equal(counts, ec), op
         if op in d.RANKED:
             assert rel_close(scores, es), op
-            if op in ("ranked_and", "ranked_or"):       # same statistics, same summation order: bit-identical
+            if op == "ranked_and":       # same statistics, same summation order: bit-identical (ranked_or runs on the union kernel: 1e-5)
                 assert np.array_equal(scores.view(np.uint32), es.view(np.uint32)), op
             whole.run(op, 10)
             wids = whole.fetch_docids()
