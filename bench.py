@@ -14,7 +14,7 @@ cpu_baseline  the reference's own operators (oracle/_ref/ref_tool, compiled from
           host cores over the same 10k queries, same index file; plus the single-thread op_perftest protocol
           (queries.cpp:13-62: 3 passes, first discarded) on a 1000-query prefix.
 parity  every query of the step against the reference's own results (-ffp-contract=off build), per operator.
-also    wand, maxscore (same protocol); decode = BASELINE config 2 (batched decode of all 1M lists, block_optpfor and
+also    wand, maxscore, or, ranked_or (same protocol); decode = BASELINE config 2 (batched decode of all 1M lists, block_optpfor and
         block_interpolative, checksum of all postings + bit-exact sample vs the reference, reference scan on 1 thread and all
         cores beside it); pef = config 3 (`opt` index of the same collection: full scans and next_geq sweeps); opt = the
         query operators over the `opt` index.  N = 1 only.
@@ -468,7 +468,7 @@ def main():
     m = measure(args.op, queries, shard_sizes)
     also_m = {}
     if args.op == "ranked_and" and not args.no_also:
-        for op2 in ("wand", "maxscore"):
+        for op2 in ("wand", "maxscore") + (("or", "ranked_or") if world == 1 else ()):
             also_m[op2] = measure(op2, queries, shard_sizes)            # the second half of BASELINE.json's metric, same protocol
     strong_m = None
     if world > 1 and args.scaling == "weak" and not args.no_also:
@@ -516,13 +516,13 @@ def main():
             line["cpu_baseline"] = cpu_baseline_for(paths, args.op, nq)
             line["parity"] = parity_block(d, paths, args.op, args.k, qidx, m["counts"], m["scores"])
             for op2, m2 in also_m.items():
-                line["also"][op2]["cpu_baseline"] = cpu_baseline_for(paths, op2, nq)
+                line["also"][op2]["cpu_baseline"] = cpu_baseline_for(paths, op2, nq, single_prefix=200 if op2 in ("or", "ranked_or") else 1000)
                 line["also"][op2]["parity"] = parity_block(d, paths, op2, args.k, qidx, m2["counts"], m2["scores"])
             # the same roofline with the bytes the REFERENCE algorithm decodes (its own block_profiler) instead of the
             # device counters: what SURVEY.md 8d defines as algorithmic bytes
             for op2, tgt in [(args.op, line)] + [(o, line["also"][o]) for o in also_m]:
                 try:
-                    prof = reference_block_profile(paths, op2, 2000)
+                    prof = reference_block_profile(paths, op2, 500 if op2 in ("or", "ranked_or") else 2000)
                     kern = tgt["roofline"]["kernel_ms"]
                     prof["achieved_GBps"] = prof["bytes_per_query"] * nq / (kern * 1e-3) / 1e9
                     prof["frac"] = prof["achieved_GBps"] / peak

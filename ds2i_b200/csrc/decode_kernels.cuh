@@ -19,6 +19,8 @@ struct DecodeJob {
     uint32_t* out_freqs;
     uint64_t total_blocks;
     uint32_t nterms;
+    const uint32_t* tail_order;   // nterms: positions of the job's lists ordered by the size of their partial last block (nullable)
+    uint32_t tail_first, tail_count;   // the slice of tail_order a launch of the tail kernel covers
 };
 
 constexpr size_t DECODE_WARP_BYTES = 2 * BLOCK * 4 + STAGE_WORDS * 4 + SCRATCH_WORDS * 4 + 16;

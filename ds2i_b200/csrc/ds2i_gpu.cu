@@ -1156,21 +1156,23 @@ constexpr size_t SINGLE_LIST_WARP_BYTES = sizeof(ListState) + STAGE_WORDS * 4 + 
 // index codes full blocks with another codec, so only the last, partial block of a list is bit-serial (thread i <-> list i);
 // otherwise (block_interpolative) thread g <-> the g-th block of the job.
 constexpr int SERIAL_WARPS = 2;
-constexpr size_t SERIAL_WARP_BYTES = size_t(BLOCK) * SERIAL_STRIDE * 4;
+__host__ __device__ constexpr size_t serial_warp_bytes(uint32_t rows) { return size_t(rows) * SERIAL_STRIDE * 4; }
 
-template <bool TAILS_ONLY>
+// ROWS: values per lane column of the transposition buffer (tails of up to 64 values run with half the shared memory, twice the warps)
+template <bool TAILS_ONLY, uint32_t ROWS>
 __global__ void __launch_bounds__(SERIAL_WARPS * 32) decode_serial_blocks_kernel(DevIndex idx, DecodeJob job) {
     const unsigned lane = lane_id();
-    uint32_t* buf = reinterpret_cast<uint32_t*>(g_smem) + (threadIdx.x >> 5) * (SERIAL_WARP_BYTES / 4);
+    uint32_t* buf = reinterpret_cast<uint32_t*>(g_smem) + (threadIdx.x >> 5) * (serial_warp_bytes(ROWS) / 4);
     uint32_t* col = buf + lane;
     const uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     uint32_t lo = 0, b = 0, size = 0;
     ListDir d{};
     bool valid;
     if (TAILS_ONLY) {
-        valid = g < job.nterms;
+        valid = g < job.tail_count;
         if (valid) {
-            lo = uint32_t(g);
+            // neighbouring lanes take tails of similar size (the loop below runs as long as the warp's longest block)
+            lo = job.tail_order ? job.tail_order[job.tail_first + g] : uint32_t(job.tail_first + g);
             d = idx.dir[job.terms[lo]];
             valid = d.n % BLOCK != 0;
             b = (d.n + BLOCK - 1) / BLOCK - 1;
@@ -1274,6 +1276,18 @@ static int decode_lists_impl(ds2i_gpu_index* ix, const uint32_t* terms, size_t n
         pef_items_guard.p = pef_items;
         if (prc) return prc;
     }
+    // the bit-serial tails of a block index, ordered by size (stable counting sort): a warp then decodes blocks of one length
+    dev_buf<uint32_t> d_order;
+    uint32_t tail_bounds[2] = {0, 0};        // first list with a tail; first list with a tail of more than 64 values
+    if (ix->kind != KIND_PEF && ix->codec != CODEC_INTERPOLATIVE && nterms) {
+        std::vector<uint32_t> order(nterms), start(BLOCK + 1, 0);
+        for (size_t i = 0; i < nterms; ++i) start[(list_size_of(ix, terms[i]) % BLOCK) + 1] += 1;
+        for (uint32_t t = 0; t < BLOCK; ++t) start[t + 1] += start[t];
+        tail_bounds[0] = start[1]; tail_bounds[1] = start[65];
+        for (size_t i = 0; i < nterms; ++i) order[start[list_size_of(ix, terms[i]) % BLOCK]++] = uint32_t(i);
+        CUDA_TRY(d_order.upload(order));
+        CUDA_TRY(cudaStreamSynchronize(0));      // `order` dies with this scope
+    }
     cuda_event ev0, ev1;
     CUDA_TRY(ev0.create()); CUDA_TRY(ev1.create());
     cudaEvent_t e0 = ev0.e, e1 = ev1.e;
@@ -1283,7 +1297,7 @@ static int decode_lists_impl(ds2i_gpu_index* ix, const uint32_t* terms, size_t n
         if (ix->kind == KIND_PEF) {
             pef_decode_launch(*ix->pef, pef_items, pef_nitems, d_terms.p, d_offs.p, d_docs.p, d_freqs.p, ix->sm_count);
         } else {
-            DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms)};
+            DecodeJob job{d_terms.p, d_blk.p, d_offs.p, d_docs.p, d_freqs.p, blk[nterms], uint32_t(nterms), d_order.p, 0u, uint32_t(nterms)};
             uint64_t want = (blk[nterms] / 32 + 4) / 4;
             int grid = int(std::min<uint64_t>(want, uint64_t(ix->sm_count) * 8));
             const size_t dsmem = S16_TAB_BYTES + 4 * DECODE_WARP_BYTES;
@@ -1295,9 +1309,21 @@ static int decode_lists_impl(ds2i_gpu_index* ix, const uint32_t* terms, size_t n
                 default: break;      // block_interpolative: every block is bit-serial
             }
             const int st = SERIAL_WARPS * 32;
-            const size_t ssmem = SERIAL_WARPS * SERIAL_WARP_BYTES;
-            if (ix->codec == CODEC_INTERPOLATIVE) decode_serial_blocks_kernel<false><<<unsigned((blk[nterms] + st - 1) / st), st, ssmem>>>(ix->dev, job);
-            else decode_serial_blocks_kernel<true><<<unsigned((nterms + st - 1) / st), st, ssmem>>>(ix->dev, job);
+            if (ix->codec == CODEC_INTERPOLATIVE) {
+                decode_serial_blocks_kernel<false, BLOCK><<<unsigned((blk[nterms] + st - 1) / st), st, SERIAL_WARPS * serial_warp_bytes(BLOCK)>>>(ix->dev, job);
+            } else {
+                // tails in order of size: [no tail][1 .. 64 values][65 .. 127 values]
+                auto slice = [&](uint32_t first, uint32_t count, bool small) {
+                    if (!count) return;
+                    DecodeJob j2 = job;
+                    j2.tail_first = first; j2.tail_count = count;
+                    const unsigned grid = unsigned((count + st - 1) / st);
+                    if (small) decode_serial_blocks_kernel<true, 64><<<grid, st, SERIAL_WARPS * serial_warp_bytes(64)>>>(ix->dev, j2);
+                    else decode_serial_blocks_kernel<true, BLOCK><<<grid, st, SERIAL_WARPS * serial_warp_bytes(BLOCK)>>>(ix->dev, j2);
+                };
+                slice(tail_bounds[0], tail_bounds[1] - tail_bounds[0], true);
+                slice(tail_bounds[1], uint32_t(nterms) - tail_bounds[1], false);
+            }
         }
     }
     CUDA_TRY(cudaEventRecord(e1));
