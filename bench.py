@@ -358,7 +358,7 @@ def main():
     def shard_for(total):
         """This rank's cost-balanced share of the first `total` queries of the file (+ the shard sizes of all ranks)."""
         allq = d.read_queries(paths["queries"], total)
-        shards = balanced_shards(query_costs(index, allq), world)
+        shards = balanced_shards(query_costs(index, allq, "conjunctive" if args.op in ("and", "ranked_and") else "postings"), world)
         return [allq[i] for i in shards[rank]], [len(s) for s in shards], np.asarray(shards[rank])
 
     log("[bench] rank %d: index in HBM (%.1f MB) in %.1f s" % (rank, index.device_bytes() / 1e6, time.time() - t0))
@@ -385,7 +385,7 @@ def main():
             if pending[j] is not None:
                 pending[j].wait()                             # stream-level: the gather that last used this buffer pair (two steps ago)
             send[j].copy_(batch.device_fused(pad_to=pad), non_blocking=True)
-            pending[j] = dist.all_gather_into_tensor(gathered[j], send[j], async_op=True)      # the ONE collective of the step
+            pending[j] = dist.all_gather_into_tensor(gathered[j].view(-1), send[j], async_op=True)      # the ONE collective of the step
             return None
 
         def drain():
@@ -419,6 +419,12 @@ def main():
         batch.run(op, args.k)                                  # instrumented launch of the same batch: the counters of SURVEY 8d
         stats = batch.stats()
         counts, scores = batch.fetch()
+        rank_kernel_ms = [sum(kernel_ms) / len(kernel_ms)]
+        if world > 1:                                          # every rank's kernel time: the step waits for the slowest shard
+            tk = torch.tensor(rank_kernel_ms, dtype=torch.float64, device="cuda")
+            allk = torch.empty((world,), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allk, tk)
+            rank_kernel_ms = [float(x) for x in allk.cpu()]
         gathered_ok = None
         if world > 1:
             # the gathered buffer of the last step holds every shard's rows: check this rank's own slice
@@ -447,7 +453,7 @@ def main():
         nterms = sum(len(q) for q in queries)
         batch.close()
         return {"total_ms": total_ms, "kernel_ms": kernel_ms, "stats": stats, "launches": launches, "counts": counts, "scores": scores,
-                "clocks": clocks.summary(), "e2e_s": e2e_s, "nq": len(queries), "gathered_ok": gathered_ok,
+                "clocks": clocks.summary(), "e2e_s": e2e_s, "nq": len(queries), "gathered_ok": gathered_ok, "rank_kernel_ms": rank_kernel_ms,
                 "h2d": nterms * 4 + (len(queries) + 1) * 8, "d2h": len(queries) * 8 + (len(queries) * args.k * 4 if op in d.RANKED else 0)}
 
     def roofline_of(m, op):
@@ -484,7 +490,7 @@ def main():
         ms_per_step = mm["total_ms"] / args.steps
         return {"metric": METRIC % (op, itype), "value": nq_total / (ms_per_step * 1e-3), "unit": "queries/s", "ms_per_step": ms_per_step,
                 "scaling": scaling, "e2e": {"value": nq_total / mm["e2e_s"], "unit": "queries/s", "h2d_bytes_per_step": mm["h2d"], "d2h_bytes_per_step": mm["d2h"]},
-                "gpu_launches": mm["launches"], "roofline": roofline_of(mm, op), "clocks": mm["clocks"]}
+                "gpu_launches": mm["launches"], "roofline": roofline_of(mm, op), "clocks": mm["clocks"], "kernel_ms_per_rank": mm["rank_kernel_ms"]}
 
     nq_total = sum(shard_sizes)
     head = line_of(m, args.op, nq_total, args.scaling)
@@ -499,6 +505,7 @@ def main():
                    "parallelism": "queries dealt cost-balanced over %d GPU(s), index replicated, ONE NCCL all_gather of the fused per-shard results per step, "
                                   "enqueued behind the kernels without a host synchronisation" % world},
         "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+        "kernel_ms_per_rank": head["kernel_ms_per_rank"],
     }
     if m["gathered_ok"] is not None:
         line["gathered_results_ok"] = m["gathered_ok"]

@@ -56,7 +56,7 @@ struct AndJob {
     const uint32_t* gstart;      // nq+1: items before the p-th query of the processing order
     const uint32_t* item_begin;  // nq+1: first result slot of query q (results are laid out in query order)
     uint32_t nitems;
-    uint32_t chunk_blocks;     // blocks of the shortest list per item (<= 32)
+    const uint8_t* qchunk;     // nq: blocks of the shortest list per item of query q (1..32: fewer where a block is expensive to probe)
     uint32_t* work_counter;
     uint32_t* item_counts;     // nitems: matches found by the item
     uint32_t* item_sizes;      // nitems: entries in the item's partial top-k
@@ -494,7 +494,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         const uint32_t gpos = warp_upper_group(job.gstart, batch.nq, ii);
         const uint32_t q = batch.sched[gpos];
         const uint32_t chunk = ii - __ldg(job.gstart + gpos);
-        const uint32_t first_block = chunk * job.chunk_blocks;
+        const uint32_t chunk_blocks = __ldg(job.qchunk + q);
+        const uint32_t first_block = chunk * chunk_blocks;
         ii = __ldg(job.item_begin + q) + chunk;      // result slot
         const uint32_t t0 = batch.q_begin[q];
         const uint32_t nt = batch.q_begin[q + 1] - t0;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) and_block_kernel(DevIndex idx, 
         __syncwarp();
 
         const uint32_t nb0 = st[0].nblocks;
-        const uint32_t b_end = min(nb0, first_block + job.chunk_blocks);
+        const uint32_t b_end = min(nb0, first_block + chunk_blocks);
         // directory entries of the whole chunk of the driving list, one block per lane, in one round trip
         uint32_t m_max = 0, m_end = 0, first_prev_max = 0xffffffffu, first_prev_end = 0;
         {

@@ -196,11 +196,12 @@ struct ds2i_gpu_batch {
     dev_view<unsigned long long> stats;
     // block-at-a-time conjunctive path: work items = (query, chunk of blocks of its shortest list)
     dev_view<uint32_t> and_gstart, and_item_begin, and_item_counts, and_item_sizes;
+    dev_view<uint8_t> and_qchunk;
     dev_buf<float> and_item_scores;
     size_t and_item_scores_k = 0;
-    uint32_t n_and_items = 0, and_chunk = AND_CHUNK_BLOCKS;
+    uint32_t n_and_items = 0;
     // block-parallel union path (wand / maxscore): work items = (query, driving list, run of its blocks), implicit
-    dev_view<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_item_begin, un_item_sizes, un_threshold;
+    dev_view<uint32_t> un_gstart, un_gterm, un_gquery, un_gbase, un_gblocks, un_item_begin, un_item_sizes, un_threshold;
     dev_view<float> un_ub;
     dev_buf<float> un_item_scores;
     size_t un_item_scores_k = 0;      // k the partial top-k buffer was sized for
@@ -546,12 +547,30 @@ static unsigned prepare_threads(size_t nq) {
     return unsigned(std::max<size_t>(1, std::min<size_t>(host_pool::get().size(), nq / 512)));
 }
 
+#ifndef DS2I_AND_ITEM_PROBES
+#define DS2I_AND_ITEM_PROBES 128
+#endif
+#ifndef DS2I_UNION_ITEM_PROBES
+#define DS2I_UNION_ITEM_PROBES 2048
+#endif
+constexpr uint64_t AND_ITEM_PROBES = DS2I_AND_ITEM_PROBES;
+constexpr uint64_t UNION_ITEM_PROBES = DS2I_UNION_ITEM_PROBES;
+static uint32_t and_chunk_max() {        // DS2I_GPU_AND_CHUNK_BLOCKS caps the blocks per item (<= 32)
+    static const uint32_t v = [] {
+        uint32_t c = AND_CHUNK_BLOCKS;
+        if (const char* ev = getenv("DS2I_GPU_AND_CHUNK_BLOCKS")) c = std::min<uint32_t>(32, std::max<uint32_t>(1, uint32_t(atoi(ev))));
+        return c;
+    }();
+    return v;
+}
+
 // what one host thread produces for its contiguous range of queries
 struct prep_part {
     std::vector<uint32_t> term, nt;          // distinct terms (query_freqs order); distinct terms per query
     std::vector<float> q_weight, max_weight;
     std::vector<uint8_t> ord_size, ord_maxw;
     std::vector<uint64_t> cost, shortest;
+    std::vector<uint8_t> chunk;               // blocks of the driving list per conjunctive work item
     int max_terms = 1;
     int rc = DS2I_OK;
     std::string err;
@@ -600,6 +619,15 @@ static void prepare_range(const ds2i_gpu_index* ix, const ds2i_gpu_wand* wand, c
         for (uint32_t i = 0; i < ne; ++i) { out.ord_size.push_back(by_size[i].pos); out.ord_maxw.push_back(by_mw[i].pos); }
         out.cost.push_back(cost);
         out.shortest.push_back(ne ? list_blocks_of(ix, by_size[0].term) : 0);            // blocks of the driving list
+        // Work per block of the driving list ~ 1 + the blocks of every other list its 128 candidates can fall into.  An item
+        // is cut so that it holds about AND_ITEM_PROBES block probes: 32 blocks when the lists are of similar length, a few
+        // when a mid-sized list is intersected with huge ones (such items ran for milliseconds and were the tail of a batch).
+        {
+            uint64_t per_block = 1;
+            const uint64_t nb0 = ne ? std::max<uint64_t>(1, list_blocks_of(ix, by_size[0].term)) : 1;
+            for (uint32_t i = 1; i < ne; ++i) per_block += std::min<uint64_t>(BLOCK, std::max<uint64_t>(1, list_blocks_of(ix, by_size[i].term) / nb0));
+            out.chunk.push_back(uint8_t(std::min<uint64_t>(and_chunk_max(), std::max<uint64_t>(1, AND_ITEM_PROBES / per_block))));
+        }
     }
 }
 
@@ -642,7 +670,8 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     const size_t o_q_begin = lay.take((nq + 1) * 4), o_term = lay.take(T * 4), o_sched = lay.take(nq * 4), o_qw = lay.take(T * 4),
                  o_mw = lay.take(T * 4), o_os = lay.take(T), o_om = lay.take(T), o_and_gstart = lay.take((nq + 1) * 4),
                  o_and_begin = lay.take((nq + 1) * 4), o_un_gstart = lay.take((G + 1) * 4), o_un_gterm = lay.take(G * 4),
-                 o_un_gquery = lay.take(G * 4), o_un_gbase = lay.take(G * 4), o_un_begin = lay.take((nq + 1) * 4), o_un_ub = lay.take(T * 4);
+                 o_un_gquery = lay.take(G * 4), o_un_gbase = lay.take(G * 4), o_un_begin = lay.take((nq + 1) * 4), o_un_ub = lay.take(T * 4),
+                 o_qchunk = lay.take(nq), o_un_gblocks = lay.take(G * 4);
     const size_t upload_bytes = lay.bytes;
 
     std::lock_guard<std::mutex> staging_lock(ix->staging_mu);
@@ -656,6 +685,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     uint8_t* ord_size = h + o_os;
     uint8_t* ord_maxw = h + o_om;
     std::vector<uint64_t> cost(nq), shortest(nq);
+    uint8_t* qchunk = h + o_qchunk;
     {
         size_t q = 0, t = 0;
         q_begin[0] = 0;
@@ -670,7 +700,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
             for (size_t i = 0; i < pt.nt.size(); ++i, ++q) {
                 t += pt.nt[i];
                 q_begin[q + 1] = uint32_t(t);
-                cost[q] = pt.cost[i]; shortest[q] = pt.shortest[i];
+                cost[q] = pt.cost[i]; shortest[q] = pt.shortest[i]; qchunk[q] = pt.chunk[i];
             }
         }
     }
@@ -691,17 +721,14 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     }
 
     const double tp1 = now_ms();
-    // work items of the conjunctive path (DS2I_GPU_AND_CHUNK_BLOCKS: blocks of the shortest list per item, <= 32)
-    uint32_t and_chunk = AND_CHUNK_BLOCKS;
-    if (const char* ev = getenv("DS2I_GPU_AND_CHUNK_BLOCKS")) and_chunk = std::min<uint32_t>(32, std::max<uint32_t>(1, uint32_t(atoi(ev))));
-    b->and_chunk = and_chunk;
+    // work items of the conjunctive path: query q owns ceil(blocks of its shortest list / qchunk[q]) items
     uint32_t* item_begin = reinterpret_cast<uint32_t*>(h + o_and_begin);
     uint32_t* and_gstart = reinterpret_cast<uint32_t*>(h + o_and_gstart);
     {
         uint64_t nitems = 0;
         item_begin[0] = 0; and_gstart[0] = 0;
         for (size_t q = 0; q < nq; ++q) {
-            if (which & 1u) nitems += (shortest[q] + and_chunk - 1) / and_chunk;
+            if (which & 1u) nitems += (shortest[q] + qchunk[q] - 1) / qchunk[q];
             if (nitems > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many work items in one batch");
             item_begin[q + 1] = uint32_t(nitems);
         }
@@ -719,6 +746,8 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         uint32_t* gterm = reinterpret_cast<uint32_t*>(h + o_un_gterm);
         uint32_t* gquery = reinterpret_cast<uint32_t*>(h + o_un_gquery);
         uint32_t* gres = reinterpret_cast<uint32_t*>(h + o_un_gbase);
+        uint32_t* gblocks_out = reinterpret_cast<uint32_t*>(h + o_un_gblocks);
+        std::vector<uint32_t> gitem(T, 0);
         std::vector<uint32_t> gbase(T, 0), gchunks(T, 0);
         // postings per work item; DS2I_GPU_UNION_ITEM_POSTINGS overrides it (tests use a tiny value to
         // exercise the splitting path on small collections)
@@ -727,6 +756,21 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
         const uint32_t item_blocks = uint32_t(std::min<uint64_t>(1u << 20, std::max<uint64_t>(1, per_item / BLOCK)));
         b->un_item_blocks = item_blocks;
         std::vector<uint32_t> level_count(MAX_TERMS + 1, 0);
+        // The size of an item follows the size of the batch: about UNION_ITEM_PROBES block probes per item when there is
+        // plenty of work (fewer, fatter items: most items of a pruned list return at once and each costs a warp a visit),
+        // down to an eighth of that when the whole batch would otherwise be a few thousand items (a strong-scaling shard:
+        // there the longest item is the run time).  Measured on B200: 10k queries 30.7 ms at 2048 vs 33.4 at 512; 1250
+        // queries 7.0 ms at 2048 vs 5.2 at 512.
+        uint64_t union_probes = UNION_ITEM_PROBES;
+        if (which & 2u) {
+            uint64_t total = 0;
+            for (size_t q = 0; q < nq; ++q) {
+                const uint32_t t0 = q_begin[q], nt = q_begin[q + 1] - t0;
+                for (uint32_t i = 0; i < nt; ++i) total += list_blocks_of(ix, term[t0 + i]) * uint64_t(nt);
+            }
+            const uint64_t want_items = uint64_t(ix->sm_count) * 28 * 16;                     // ~16 items per resident warp
+            union_probes = std::min<uint64_t>(UNION_ITEM_PROBES, std::max<uint64_t>(UNION_ITEM_PROBES / 8, total / want_items));
+        }
         uint64_t nitems = 0;
         ubegin[0] = 0;
         for (size_t q = 0; q < nq; ++q) {
@@ -738,7 +782,14 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
                 ub[t0 + i] = acc;
                 if (!(which & 2u)) continue;
                 const uint64_t nb = list_blocks_of(ix, term[t0 + ord_maxw[t0 + i]]);
-                gchunks[t0 + i] = uint32_t((nb + item_blocks - 1) / item_blocks);
+                // blocks per item of this (query, list) group: ~UNION_ITEM_PROBES block probes (ownership probes of the lists
+                // above, completion probes of the lists below), at most item_blocks
+                uint64_t per_block = 1;
+                for (uint32_t j = 0; j < nt; ++j)
+                    if (j != i) per_block += std::min<uint64_t>(BLOCK, std::max<uint64_t>(1, list_blocks_of(ix, term[t0 + ord_maxw[t0 + j]]) / std::max<uint64_t>(nb, 1)));
+                const uint32_t ib = uint32_t(std::min<uint64_t>(item_blocks, std::max<uint64_t>(1, union_probes / per_block)));
+                gitem[t0 + i] = ib;
+                gchunks[t0 + i] = uint32_t((nb + ib - 1) / ib);
                 gbase[t0 + i] = uint32_t(nitems);
                 nitems += gchunks[t0 + i];
                 level_count[nt - 1 - i] += 1;
@@ -756,7 +807,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
                 const uint32_t t0 = q_begin[qi], nt = q_begin[qi + 1] - t0;
                 for (uint32_t i = 0; i < nt; ++i) {
                     const uint32_t pos = level_pos[nt - 1 - i]++;
-                    gterm[pos] = t0 + i; gquery[pos] = qi; gres[pos] = gbase[t0 + i]; gstart[pos + 1] = gchunks[t0 + i];
+                    gterm[pos] = t0 + i; gquery[pos] = qi; gres[pos] = gbase[t0 + i]; gstart[pos + 1] = gchunks[t0 + i]; gblocks_out[pos] = gitem[t0 + i];
                 }
             }
             for (size_t g = 0; g < G; ++g) gstart[g + 1] += gstart[g];
@@ -781,6 +832,7 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     b->un_gstart.p = reinterpret_cast<uint32_t*>(d + o_un_gstart); b->un_gterm.p = reinterpret_cast<uint32_t*>(d + o_un_gterm);
     b->un_gquery.p = reinterpret_cast<uint32_t*>(d + o_un_gquery); b->un_gbase.p = reinterpret_cast<uint32_t*>(d + o_un_gbase);
     b->un_item_begin.p = reinterpret_cast<uint32_t*>(d + o_un_begin); b->un_ub.p = reinterpret_cast<float*>(d + o_un_ub);
+    b->and_qchunk.p = d + o_qchunk; b->un_gblocks.p = reinterpret_cast<uint32_t*>(d + o_un_gblocks);
     b->work_counter.p = reinterpret_cast<uint32_t*>(d + o_counter); b->stats.p = reinterpret_cast<unsigned long long*>(d + o_stats);
     b->and_item_counts.p = reinterpret_cast<uint32_t*>(d + o_and_counts); b->and_item_sizes.p = reinterpret_cast<uint32_t*>(d + o_and_sizes);
     b->un_item_sizes.p = reinterpret_cast<uint32_t*>(d + o_un_sizes); b->un_threshold.p = reinterpret_cast<uint32_t*>(d + o_un_thr);
@@ -844,7 +896,7 @@ static int launch_and_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k) {
             CUDA_TRY(b->and_item_scores.alloc(size_t(b->n_and_items) * 2 * k));
             b->and_item_scores_k = k;
         }
-        AndJob job{b->and_gstart.p, b->and_item_begin.p, b->n_and_items, b->and_chunk, b->work_counter.p + 1, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
+        AndJob job{b->and_gstart.p, b->and_item_begin.p, b->n_and_items, b->and_qchunk.p, b->work_counter.p + 1, b->and_item_counts.p, b->and_item_sizes.p, b->and_item_scores.p};
         kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, slots);
         b->launches += 1;
     }
@@ -895,7 +947,7 @@ static int launch_union_block(ds2i_gpu_batch* b, DevBatch const& db, uint32_t k)
         b->un_item_scores_k = k;
     }
     CUDA_TRY(cudaMemsetAsync(b->un_threshold.p, 0, std::max<size_t>(b->nq, 1) * sizeof(uint32_t)));
-    UnionJob job{b->un_gstart.p, b->un_gterm.p, b->un_gquery.p, b->un_gbase.p, b->un_ub.p, b->n_un_groups, b->n_un_items, b->un_item_blocks, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
+    UnionJob job{b->un_gstart.p, b->un_gterm.p, b->un_gquery.p, b->un_gbase.p, b->un_ub.p, b->un_gblocks.p, b->n_un_groups, b->n_un_items, b->work_counter.p + 3, b->un_threshold.p, b->un_item_sizes.p, b->un_item_scores.p};
     const DevWand dw = b->wand ? b->wand->dev : DevWand{nullptr, nullptr, 0.f};
     if (b->n_un_items) { kern<<<grid, warps * 32, smem>>>(ix->dev, dw, db, job, k, b->max_terms); b->launches += 1; }
     if (MODE == UNION_COUNT) merge_union_counts_kernel<<<(b->nq + 3) / 4, 128>>>(b->un_item_begin.p, b->nq, b->un_item_sizes.p, b->out_counts.p);

@@ -40,7 +40,8 @@ struct UnionJob {
     const uint32_t* gquery;      // ngroups
     const uint32_t* gbase;       // ngroups: first result slot of the group (results are laid out in query order)
     const float* ub;             // per query term, in max_weight order: the reference's upper_bounds[] (queries.hpp:526-530)
-    uint32_t ngroups, nitems, item_blocks;
+    const uint32_t* gblocks;     // ngroups: blocks of the driving list per item of the group (fewer where a block is expensive to complete)
+    uint32_t ngroups, nitems;
     uint32_t* work_counter;
     uint32_t* query_threshold;   // nq: float bits of the best published k-th score of the query
     uint32_t* item_sizes;
@@ -180,7 +181,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
         const uint32_t g = warp_upper_group(job.gstart, job.ngroups, ii);
         const uint32_t chunk = ii - __ldg(job.gstart + g);
         const uint32_t q = __ldg(job.gquery + g);
-        const uint32_t first_block = chunk * job.item_blocks;
+        const uint32_t item_blocks = __ldg(job.gblocks + g);
+        const uint32_t first_block = chunk * item_blocks;
         const uint32_t rslot = __ldg(job.gbase + g) + chunk;       // where this item's partial top-k goes
         const uint32_t t0 = batch.q_begin[q];
         const uint32_t nt = batch.q_begin[q + 1] - t0;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) union_drive_kernel(DevIndex idx
         AndList* sd = &st[e];
         const uint2* bd0 = idx.bdir + sd->bfirst;
         const float qw_e = ws->qw[e];
-        const uint32_t b_end = min(sd->nblocks, first_block + job.item_blocks);
+        const uint32_t b_end = min(sd->nblocks, first_block + item_blocks);
         float published = topk.floor_;
         bool stop = false;
         for (uint32_t c0 = first_block; c0 < b_end && !stop; c0 += 32) {

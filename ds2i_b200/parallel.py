@@ -29,13 +29,26 @@ def balanced_shards(costs, world):
     return [order[r::world] for r in range(world)]
 
 
-def query_costs(index, queries):
-    """Postings in the lists of each query: the cost model of the scheduler (the same one the library uses to order work)."""
+def query_costs(index, queries, model="postings"):
+    """Cost of each query for the shard balancer.
+    model "postings": postings in the lists of the query (what the library's own scheduler orders work by);
+    model "conjunctive": block decodes of a conjunctive evaluation — two per block of the shortest list (docs + freqs) plus, for
+    every other list, the blocks it can be probed in: min(its blocks, 128 candidates x blocks of the shortest list).  Dealing the
+    queries by this cost spreads the heavy conjunctions (a mid-sized list against a huge one) evenly over the ranks."""
     flat = np.fromiter((t for q in queries for t in q), dtype=np.uint32)
     sizes = index.list_sizes(flat).astype(np.int64) if len(flat) else np.zeros(0, np.int64)
     bounds = np.cumsum([0] + [len(q) for q in queries])
-    csum = np.concatenate([[0], np.cumsum(sizes)])
-    return csum[bounds[1:]] - csum[bounds[:-1]]
+    if model == "postings":
+        csum = np.concatenate([[0], np.cumsum(sizes)])
+        return csum[bounds[1:]] - csum[bounds[:-1]]
+    blocks = (sizes + 127) // 128
+    out = np.zeros(len(queries), dtype=np.int64)
+    for i in range(len(queries)):
+        b = np.unique(flat[bounds[i]:bounds[i + 1]], return_index=True)[1]          # distinct terms
+        nb = np.sort(blocks[bounds[i]:bounds[i + 1]][b])
+        if len(nb):
+            out[i] = 2 * nb[0] + int(np.minimum(nb[1:], 128 * nb[0]).sum())
+    return out
 
 
 def gather_topk(counts, scores, world):
@@ -63,9 +76,9 @@ def gather_fused(fused, world, out=None):
     if world == 1:
         return fused.reshape(1, -1)
     if out is None:
-        out = torch.empty((world, fused.shape[0]), dtype=torch.uint8, device=fused.device)
-    dist.all_gather_into_tensor(out, fused)
-    return out
+        out = torch.empty((world * fused.shape[0],), dtype=torch.uint8, device=fused.device)
+    dist.all_gather_into_tensor(out.view(-1), fused)          # a flat output: gloo (the CPU tests) insists on it
+    return out.view(world, fused.shape[0])
 
 
 def split_fused(buf, nq, k):

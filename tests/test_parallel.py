@@ -100,3 +100,57 @@ def test_global_stats_exchange_world_size_2_gloo():
     out = mgr.dict()
     mp.spawn(_stats_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+# ---- the fused gather and the shard balancer (ds2i_b200/parallel.py), world_size 2 on gloo ----------------------------------
+class _SizesIndex:
+    def __init__(self, sizes):
+        import numpy as np
+        self.sizes = np.asarray(sizes, dtype=np.uint64)
+
+    def list_sizes(self, terms):
+        return self.sizes[terms]
+
+
+def test_balanced_shards_and_cost_models():
+    import numpy as np
+    from ds2i_b200.parallel import balanced_shards, query_costs
+    idx = _SizesIndex([100, 128 * 40, 128 * 5000, 300, 7])
+    qs = [[0, 2], [1, 2], [2], [3, 3, 4], []]
+    post = query_costs(idx, qs, "postings")
+    assert post.tolist() == [100 + 640000, 5120 + 640000, 640000, 300 + 300 + 7, 0]
+    conj = query_costs(idx, qs, "conjunctive")
+    # [0,2]: shortest list 1 block -> 2 + min(5000, 128); [1,2]: 40 blocks -> 80 + min(5000, 5120); [2]: 2 * 5000; [3,3,4]: distinct {3,4}: 1 block, 3 blocks
+    assert conj.tolist() == [2 + 128, 80 + 5000, 10000, 2 + 3, 0]
+    shards = balanced_shards(conj, 2)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(5)) and abs(len(shards[0]) - len(shards[1])) <= 1
+    assert shards[0][0] == 2 and shards[1][0] == 1            # the two heaviest queries go to different ranks
+
+
+def _fused_worker(rank, world, port, out):
+    import numpy as np
+    from ds2i_b200.parallel import fused_row_bytes, gather_fused, split_fused
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nq, k = 4, 3
+    counts = np.arange(nq, dtype=np.uint64) + 10 * rank
+    scores = (np.arange(nq * k, dtype=np.float32) + 100 * rank).reshape(nq, k)
+    docids = (np.arange(nq * k, dtype=np.uint32) + 1000 * rank).reshape(nq, k)
+    fused = torch.from_numpy(np.concatenate([counts.view(np.uint8), scores.reshape(-1).view(np.uint8), docids.reshape(-1).view(np.uint8)]))
+    assert fused.numel() == fused_row_bytes(nq, k)
+    allr = gather_fused(fused, world)                         # ONE collective for counts + scores + docids
+    ok = allr.shape == (world, fused_row_bytes(nq, k))
+    for r in range(world):
+        c, s, dd = split_fused(allr[r].numpy(), nq, k)
+        ok = ok and c.tolist() == (np.arange(nq) + 10 * r).tolist() and float(s[1, 2]) == 5 + 100 * r and int(dd[3, 0]) == 9 + 1000 * r
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_fused_gather_world_size_2_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fused_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
