@@ -108,13 +108,16 @@ class ClockSampler:
                 pass
 
     def __enter__(self):
+        if os.environ.get("DS2I_BENCH_NO_CLOCKS"):        # diagnostic: is the NVML polling itself in the way?
+            return self
         self.t.start()
         time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.t.join(timeout=6)
+        if self.t.is_alive():
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.samples:
@@ -367,8 +370,12 @@ def main():
         """W warm-up + K timed steps of `op` over the resident batch, then the end-to-end leg."""
         batch = d.QueryBatch(idx, wdata, queries)
         pad = max(shard_sizes) * (8 + 8 * args.k) if op in d.RANKED else max(shard_sizes) * 8
-        # the gather of step t overlaps the kernels of step t + 1: the fused results are copied (device to device, on the kernels'
-        # stream) into one of two send buffers and all-gathered from there asynchronously on NCCL's stream
+        # ONE collective per step, in line with the kernels: the fused result buffer is all-gathered right behind the launch, on
+        # NCCL's stream, and the next step's kernels wait for it (measured at 4 GPUs: 0.03 ms per 15 ms step).  Overlapping the
+        # gather of step t with the kernels of step t + 1 (two send buffers, async_op=True; DS2I_BENCH_OVERLAP_GATHER=1) was built
+        # and measured too and is SLOWER (+0.5 ms per step): the persistent query kernels fill every SM, so NCCL's kernels only
+        # get scheduled in the tail of the next step anyway, and the ranks end up coupled more tightly, not less.
+        overlap = bool(os.environ.get("DS2I_BENCH_OVERLAP_GATHER"))
         send = [torch.empty((pad,), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
         gathered = [torch.empty((world, pad), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
         pending = [None, None]
@@ -382,10 +389,13 @@ def main():
             batch.run(op, args.k, wait=False, stats=False)    # no host synchronisation inside a step
             j = nstep[0] & 1
             nstep[0] += 1
+            if not overlap:
+                dist.all_gather_into_tensor(gathered[j].view(-1), batch.device_fused(pad_to=pad))      # the ONE collective of the step
+                return None
             if pending[j] is not None:
                 pending[j].wait()                             # stream-level: the gather that last used this buffer pair (two steps ago)
             send[j].copy_(batch.device_fused(pad_to=pad), non_blocking=True)
-            pending[j] = dist.all_gather_into_tensor(gathered[j].view(-1), send[j], async_op=True)      # the ONE collective of the step
+            pending[j] = dist.all_gather_into_tensor(gathered[j].view(-1), send[j], async_op=True)
             return None
 
         def drain():
