@@ -360,8 +360,12 @@ def main():
 
     def shard_for(total):
         """This rank's cost-balanced share of the first `total` queries of the file (+ the shard sizes of all ranks)."""
-        allq = d.read_queries(paths["queries"], total)
-        shards = balanced_shards(query_costs(index, allq, "conjunctive" if args.op in ("and", "ranked_and") else "postings"), world)
+        emu = os.environ.get("DS2I_BENCH_EMULATE_SHARD")                   # diagnostic, 1 GPU: "r/W" = run the shard rank r of a W-GPU weak run has
+        r, w = (int(x) for x in emu.split("/")) if emu and world == 1 else (rank, world)
+        allq = d.read_queries(paths["queries"], total * (w if emu and world == 1 else 1))
+        shards = balanced_shards(query_costs(index, allq, "conjunctive" if args.op in ("and", "ranked_and") else "postings"), w)
+        if w != world:
+            return [allq[i] for i in shards[r]], [len(shards[r])], np.asarray(shards[r])
         return [allq[i] for i in shards[rank]], [len(s) for s in shards], np.asarray(shards[rank])
 
     log("[bench] rank %d: index in HBM (%.1f MB) in %.1f s" % (rank, index.device_bytes() / 1e6, time.time() - t0))
