@@ -65,9 +65,10 @@ static void tune_mem_pool(int device) {
 // of one process (ds2i_gpu_query_batch_multi), and stream 0 / cudaFreeAsync act on the CURRENT device
 struct device_scope {
     int prev = -1;
+    cudaError_t status = cudaSuccess;           // of the switch: CUDA_TRY(scope.status) where a wrong device must not go unnoticed
     explicit device_scope(int device) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != device) cudaSetDevice(device); else prev = -1;
+        if (prev != device) status = cudaSetDevice(device); else prev = -1;
     }
     ~device_scope() { if (prev >= 0) cudaSetDevice(prev); }
 };
@@ -255,7 +256,8 @@ extern "C" int ds2i_gpu_index_open(const void* file_bytes, size_t nbytes, const 
     int kind;
     int codec = codec_from_type(index_type, &kind);
     if (codec < 0) return fail(DS2I_E_UNSUPPORTED, std::string("unsupported index type ") + index_type);
-    CUDA_TRY(cudaSetDevice(device));
+    device_scope on_device(device);
+    CUDA_TRY(on_device.status);
     std::unique_ptr<ds2i_gpu_index> ix(new ds2i_gpu_index);
     ix->device = device; ix->kind = kind; ix->codec = codec;
     cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -389,7 +391,8 @@ extern "C" int ds2i_gpu_index_list_bytes(const ds2i_gpu_index* ix, const uint32_
 
 extern "C" int ds2i_gpu_wand_open(const void* file_bytes, size_t nbytes, int device, ds2i_gpu_wand** out) {
     if (!file_bytes || !out) return fail(DS2I_E_ARG, "null argument");
-    CUDA_TRY(cudaSetDevice(device));
+    device_scope on_device(device);
+    CUDA_TRY(on_device.status);
     std::unique_ptr<ds2i_gpu_wand> w(new ds2i_gpu_wand);
     w->device = device;
     try {
@@ -642,7 +645,8 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     if (!ix || !out || !query_offsets || (!terms && nq && query_offsets[nq])) return fail(DS2I_E_ARG, "null argument");
     if (nq > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many queries in one batch");
     if (wand && wand->num_docs < ix->num_docs) return fail(DS2I_E_ARG, "wand data has fewer documents than the index");
-    CUDA_TRY(cudaSetDevice(ix->device));
+    device_scope on_device(ix->device);
+    CUDA_TRY(on_device.status);
     std::unique_ptr<ds2i_gpu_batch> b(new ds2i_gpu_batch);
     b->index = ix; b->wand = wand; b->nq = uint32_t(nq); b->items_built = which;
     const double tp0 = now_ms();
@@ -1002,7 +1006,8 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     if (ranked && !b->wand) return fail(DS2I_E_ARG, "ranked operators need wand data");
     if (ranked && (k < 1 || k > MAX_K)) return fail(DS2I_E_LIMIT, "k must be in 1.." + std::to_string(MAX_K));
     ds2i_gpu_index* ix = b->index;
-    CUDA_TRY(cudaSetDevice(ix->device));
+    device_scope on_device(ix->device);
+    CUDA_TRY(on_device.status);
     if (!ranked) k = 1;
     b->layout_outputs(k);
     DevBatch db{};
@@ -1056,7 +1061,8 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
 extern "C" int ds2i_gpu_batch_wait(ds2i_gpu_batch* b, float* out_elapsed_ms) {
     if (!b) return fail(DS2I_E_ARG, "null batch");
     if (!b->pending) { if (out_elapsed_ms) *out_elapsed_ms = 0.f; return DS2I_OK; }
-    CUDA_TRY(cudaSetDevice(b->index->device));
+    device_scope on_device(b->index->device);
+    CUDA_TRY(on_device.status);
     CUDA_TRY(cudaEventSynchronize(b->ev1));
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
@@ -1079,7 +1085,8 @@ extern "C" int ds2i_gpu_batch_wait(ds2i_gpu_batch* b, float* out_elapsed_ms) {
 
 extern "C" int ds2i_gpu_batch_fetch(ds2i_gpu_batch* b, uint64_t* out_counts, float* out_scores) {
     if (!b) return fail(DS2I_E_ARG, "null batch");
-    CUDA_TRY(cudaSetDevice(b->index->device));
+    device_scope on_device(b->index->device);
+    CUDA_TRY(on_device.status);
     if (out_counts && b->nq) CUDA_TRY(cudaMemcpy(out_counts, b->out_counts.p, size_t(b->nq) * 8, cudaMemcpyDeviceToHost));
     if (out_scores && b->nq && b->last_ranked)
         CUDA_TRY(cudaMemcpy(out_scores, b->out_scores.p, size_t(b->nq) * b->last_k * 4, cudaMemcpyDeviceToHost));
@@ -1089,14 +1096,16 @@ extern "C" int ds2i_gpu_batch_fetch(ds2i_gpu_batch* b, uint64_t* out_counts, flo
 extern "C" int ds2i_gpu_batch_fetch_docids(ds2i_gpu_batch* b, uint32_t* out_docids) {
     if (!b || !out_docids) return fail(DS2I_E_ARG, "null argument");
     if (!b->last_ranked) return fail(DS2I_E_ARG, "the last operator run on this batch was not a ranked one");
-    CUDA_TRY(cudaSetDevice(b->index->device));
+    device_scope on_device(b->index->device);
+    CUDA_TRY(on_device.status);
     if (b->nq) CUDA_TRY(cudaMemcpy(out_docids, b->out_docids.p, size_t(b->nq) * b->last_k * 4, cudaMemcpyDeviceToHost));
     return DS2I_OK;
 }
 
 extern "C" int ds2i_gpu_batch_stats(ds2i_gpu_batch* b, uint64_t out_stats[8]) {
     if (!b || !out_stats) return fail(DS2I_E_ARG, "null argument");
-    CUDA_TRY(cudaSetDevice(b->index->device));
+    device_scope on_device(b->index->device);
+    CUDA_TRY(on_device.status);
     unsigned long long s[8];
     CUDA_TRY(cudaMemcpy(s, b->stats.p, sizeof(s), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) out_stats[i] = s[i];
@@ -1306,7 +1315,8 @@ static int decode_lists_impl(ds2i_gpu_index* ix, const uint32_t* terms, size_t n
                              uint32_t* out_freqs, uint64_t* out_sums, float* out_elapsed_ms) {
     if (!ix || (!terms && nterms) || !out_offsets) return fail(DS2I_E_ARG, "null argument");
     if (nterms > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many lists");
-    CUDA_TRY(cudaSetDevice(ix->device));
+    device_scope on_device(ix->device);
+    CUDA_TRY(on_device.status);
     std::vector<uint64_t> blk(nterms + 1, 0), offs(out_offsets, out_offsets + nterms + 1);
     for (size_t i = 0; i < nterms; ++i) {
         if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
@@ -1447,7 +1457,8 @@ extern "C" int ds2i_gpu_next_geq_batch(ds2i_gpu_index* ix, const uint32_t* terms
                                        uint64_t* out_docids, uint64_t* out_freqs, float* out_elapsed_ms) {
     if (!ix || (!terms && nlists) || !bound_offsets) return fail(DS2I_E_ARG, "null argument");
     if (nlists > 0x7fffffffull) return fail(DS2I_E_LIMIT, "too many lists");
-    CUDA_TRY(cudaSetDevice(ix->device));
+    device_scope on_device(ix->device);
+    CUDA_TRY(on_device.status);
     for (size_t i = 0; i < nlists; ++i)
         if (terms[i] >= ix->size) return fail(DS2I_E_ARG, "term id out of range");
     const uint64_t total = nlists ? bound_offsets[nlists] : 0;
@@ -1524,6 +1535,7 @@ struct ds2i_gpu_group {
     std::vector<ncclComm_t> comms;              // empty for a single device
     dev_buf<uint8_t> gathered;                  // on devices[0]: the fused results of every shard, back to back
     pinned_arena host;                          // D2H staging of the gathered results
+    std::mutex mu;                              // one batch at a time per group (gathered / host are per group)
     ~ds2i_gpu_group() {
         for (ncclComm_t c : comms) if (c) g_nccl.CommDestroy(c);
         for (auto* w : wands) ds2i_gpu_wand_close(w);
@@ -1585,16 +1597,33 @@ extern "C" int ds2i_gpu_group_query_batch(ds2i_gpu_group* g, int op, uint32_t k,
     const size_t G = g->devices.size();
     const uint32_t kk = ranked ? k : 0;
 
-    // cost-balanced shards: queries sorted by the postings of their lists, dealt round-robin (shard sizes differ by <= 1)
+    std::lock_guard<std::mutex> lock(g->mu);
+    device_scope scope(g->devices[0]);          // the caller's current device is restored on every return path ...
+    struct first_device { int d; ~first_device() { cudaSetDevice(d); } } back_to_first{g->devices[0]};     // ... also after the per-device waits below
+
+    // cost-balanced shards: queries sorted by estimated cost, dealt round-robin (shard sizes differ by <= 1).  Cost of a
+    // conjunctive query = block decodes of its evaluation: two per block of the shortest list (docs + freqs) plus, for every
+    // other list, the blocks it can be probed in, min(its blocks, 128 candidates x blocks of the shortest list); of any other
+    // query = the postings of its lists.  (ds2i_b200/parallel.py query_costs is the same model for torch.distributed hosts.)
     std::vector<uint32_t> order(nq);
     {
         ds2i_gpu_index* ix0 = g->indexes[0];
-        std::vector<uint64_t> cost(nq, 0);
+        const bool conjunctive = op == OP_AND || op == OP_RANKED_AND || op == OP_AND_FREQ;
+        std::vector<uint64_t> cost(nq, 0), nb;
         for (size_t q = 0; q < nq; ++q) {
             if (query_offsets[q + 1] < query_offsets[q]) return fail(DS2I_E_ARG, "query_offsets not monotone");
+            nb.clear();
             for (uint64_t j = query_offsets[q]; j < query_offsets[q + 1]; ++j) {
                 if (terms[j] >= ix0->size) return fail(DS2I_E_ARG, "term id out of range in query " + std::to_string(q));
-                cost[q] += list_size_of(ix0, terms[j]);
+                const uint64_t n = list_size_of(ix0, terms[j]);
+                if (!conjunctive) { cost[q] += n; continue; }
+                if (std::find(terms + query_offsets[q], terms + j, terms[j]) == terms + j) nb.push_back((n + 127) / 128);    // distinct terms
+            }
+            if (conjunctive && !nb.empty()) {
+                const uint64_t shortest = *std::min_element(nb.begin(), nb.end());
+                uint64_t c = 0;
+                for (uint64_t b : nb) c += std::min<uint64_t>(b, 128 * shortest);
+                cost[q] = c - std::min<uint64_t>(shortest, 128 * shortest) + 2 * shortest;
             }
         }
         std::iota(order.begin(), order.end(), 0u);
@@ -1622,7 +1651,7 @@ extern "C" int ds2i_gpu_group_query_batch(ds2i_gpu_group* g, int op, uint32_t k,
         static const uint32_t no_terms = 0;
         const uint32_t* tp = shard_terms[s].empty() ? &no_terms : shard_terms[s].data();
         rcs[s] = batch_prepare_impl(g->indexes[s], g->wands.empty() ? nullptr : g->wands[s], tp, shard_offs[s].data(), shard_q[s].size(), which, &batches[s]);
-        if (rcs[s] == DS2I_OK) rcs[s] = ds2i_gpu_batch_run_ex(batches[s], op, k, 0u, &kernel_ms[s]);
+        if (rcs[s] == DS2I_OK) rcs[s] = ds2i_gpu_batch_run_ex(batches[s], op, k, DS2I_RUN_NO_STATS, &kernel_ms[s]);     // the batch dies with the call
         if (rcs[s] != DS2I_OK) errs[s] = ds2i_gpu_last_error();
     };
     {
