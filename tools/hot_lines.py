@@ -9,21 +9,30 @@ td = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.join(ROOT, 'ds2i_b200', 'lib', 'libds2i_gpu.so')], cwd=td, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(td) if f.endswith('.cubin')][0]
 dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(td, cubin)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout.splitlines()
-seq, cur, on = [], None, False
+rows = list(csv.reader(io.StringIO(subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout)))
+hdr, data = rows[1], rows[2:]
+ia, isamp = hdr.index('Instructions Executed'), hdr.index('# Samples')
+# every .text section whose name holds the pattern (template instances share a prefix); the one with as many SASS
+# instructions as the report is the captured kernel
+sections, cur, name = {}, None, None
 for line in dis:
     if line.startswith('\t.section\t.text.') or line.startswith('.section'):
-        on = pat in line
-    if not on:
+        name = line.split()[1].split(',')[0] if pat in line and '.text.' in line else None
+        if name:
+            sections[name] = []
+        continue
+    if name is None:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', line)
     if m:
         cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);', line)
     if m:
-        seq.append(cur)
-rows = list(csv.reader(io.StringIO(subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout)))
-hdr, data = rows[1], rows[2:]
-ia, isamp = hdr.index('Instructions Executed'), hdr.index('# Samples')
+        sections[name].append(cur)
+exact = [k for k, v in sections.items() if len(v) == len(data)]
+pick = exact[0] if exact else (next(iter(sections)) if sections else None)
+seq = sections.get(pick, [])
+print('kernel section %s (%d candidates for the pattern)' % (pick, len(sections)))
 if len(seq) != len(data):
     print('WARNING: %d SASS instructions in the cubin vs %d in the report (rebuild mismatch?)' % (len(seq), len(data)))
 n = min(len(seq), len(data))
