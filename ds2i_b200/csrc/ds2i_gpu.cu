@@ -584,7 +584,11 @@ static void prepare_range(const ds2i_gpu_index* ix, const ds2i_gpu_wand* wand, c
     struct ent { uint64_t n; float mw; uint8_t pos; uint64_t local_n; uint32_t term; };   // n: the list size the reference would see (collection-wide df for a shard)
     std::vector<uint32_t> tmp;
     ent ents[MAX_TERMS], by_size[MAX_TERMS], by_mw[MAX_TERMS];
-    out.nt.reserve(q1 - q0); out.cost.reserve(q1 - q0); out.shortest.reserve(q1 - q0);
+    out.nt.reserve(q1 - q0); out.cost.reserve(q1 - q0); out.shortest.reserve(q1 - q0); out.chunk.reserve(q1 - q0);
+    {
+        const size_t nt_max = q1 > q0 && query_offsets[q1] >= query_offsets[q0] ? size_t(query_offsets[q1] - query_offsets[q0]) : 0;
+        out.term.reserve(nt_max); out.q_weight.reserve(nt_max); out.max_weight.reserve(nt_max); out.ord_size.reserve(nt_max); out.ord_maxw.reserve(nt_max);
+    }
     for (size_t q = q0; q < q1; ++q) {
         if (query_offsets[q + 1] < query_offsets[q]) { out.rc = DS2I_E_ARG; out.err = "query_offsets not monotone"; return; }
         tmp.assign(terms + query_offsets[q], terms + query_offsets[q + 1]);
@@ -742,8 +746,10 @@ static int batch_prepare_impl(ds2i_gpu_index* ix, ds2i_gpu_wand* wand, const uin
     }
 
     // work items of the union path: (query, driving list, run of its blocks), highest-weight lists first.  Only the
-    // groups (one per query term) are materialised; the kernel derives the items from the prefix array.
-    {
+    // groups (one per query term) are materialised; the kernel derives the items from the prefix array.  (A batch prepared
+    // for the conjunctive operators alone, which == 1, is only ever run with those: it needs neither the items nor the
+    // upper-bound prefix sums of wand / maxscore.)
+    if (which != 1u) {
         float* ub = reinterpret_cast<float*>(h + o_un_ub);
         uint32_t* ubegin = reinterpret_cast<uint32_t*>(h + o_un_begin);
         uint32_t* gstart = reinterpret_cast<uint32_t*>(h + o_un_gstart);
@@ -1005,6 +1011,7 @@ extern "C" int ds2i_gpu_batch_run_ex(ds2i_gpu_batch* b, int op, uint32_t k, uint
     const bool ranked = op >= OP_RANKED_AND;
     if (ranked && !b->wand) return fail(DS2I_E_ARG, "ranked operators need wand data");
     if (ranked && (k < 1 || k > MAX_K)) return fail(DS2I_E_LIMIT, "k must be in 1.." + std::to_string(MAX_K));
+    if (b->items_built == 1u && op != OP_AND && op != OP_RANKED_AND) return fail(DS2I_E_ARG, "batch was prepared for the conjunctive operators only");
     ds2i_gpu_index* ix = b->index;
     device_scope on_device(ix->device);
     CUDA_TRY(on_device.status);
